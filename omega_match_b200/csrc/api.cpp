@@ -1,0 +1,289 @@
+// api.cpp -- the C ABI of libomega_match.so (declarations and reference citations:
+// include/olm_b200.h).  Thin: argument checking, file handling, and calls into Engine.
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+
+#include "../../include/olm_b200.h"
+#include "engine.h"
+#include "host_util.h"
+#include "store.h"
+
+#ifndef OLM_B200_VERSION
+#define OLM_B200_VERSION "0.1.0"
+#endif
+
+struct omega_list_matcher_struct {
+  olm::Engine *engine = nullptr;
+  uint8_t *file = nullptr; // mapped store
+  size_t file_size = 0;
+  char *temp_path = nullptr; // set when the store was compiled on the fly (matcher.c:458-481)
+  omega_match_stats_t *stats = nullptr;
+  int threads = 1;
+  int chunk = 4096;
+};
+
+namespace {
+
+int g_default_device = -1;
+
+int default_device() {
+  if (g_default_device >= 0) return g_default_device;
+  if (const char *e = std::getenv("OLM_CUDA_DEVICE")) return std::atoi(e);
+  return 0;
+}
+
+int max_host_threads() {
+  const unsigned n = std::thread::hardware_concurrency();
+  return n ? int(n) : 1;
+}
+
+// 1234567 -> "1,234,567" (what the reference's header line prints, util.h:28-58)
+std::string with_commas(uint64_t v) {
+  std::string s = std::to_string(v);
+  for (int i = int(s.size()) - 3; i > 0; i -= 3) s.insert(size_t(i), ",");
+  return s;
+}
+
+olm::MatchFlags to_flags(int no_overlap, int longest_only, int word_boundary, int word_prefix, int word_suffix,
+                         int line_start, int line_end) {
+  olm::MatchFlags f;
+  f.no_overlap = no_overlap != 0;
+  f.longest_only = longest_only != 0;
+  f.word_boundary = word_boundary != 0;
+  f.word_prefix = word_prefix != 0;
+  f.word_suffix = word_suffix != 0;
+  f.line_start = line_start != 0;
+  f.line_end = line_end != 0;
+  return f;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *omega_match_version(void) { return OLM_B200_VERSION; }
+
+omega_list_matcher_t *omega_list_matcher_create(const char *path, int case_insensitive, int ignore_punctuation,
+                                                int elide_whitespace, omega_match_pattern_store_stats_t *stats) {
+  if (!path) return nullptr;
+  std::string load = path;
+  char *temp_path = nullptr;
+  if (!omega_list_matcher_is_compiled(path)) {
+    char tmp[] = "/tmp/oa_matcher_XXXXXX";
+    const int fd = mkstemp(tmp);
+    if (fd < 0) {
+      std::perror("mkstemp");
+      return nullptr;
+    }
+    close(fd);
+    if (omega_list_matcher_compile_patterns_filename(tmp, path, case_insensitive, ignore_punctuation,
+                                                     elide_whitespace, stats) != 0) {
+      unlink(tmp);
+      return nullptr;
+    }
+    temp_path = strdup(tmp);
+    load = tmp;
+  }
+  auto *m = new omega_list_matcher_struct();
+  m->temp_path = temp_path;
+  m->file = olm::map_whole_file(load.c_str(), &m->file_size, false);
+  std::string err = "cannot map file";
+  if (m->file) m->engine = olm::Engine::create(m->file, m->file_size, default_device(), &err);
+  if (!m->engine) {
+    std::fprintf(stderr, "libomega_match(b200): cannot create matcher from %s: %s\n", path, err.c_str());
+    omega_list_matcher_destroy(m);
+    return nullptr;
+  }
+  omega_matcher_set_num_threads(m, 0); // matcher.c:509-511
+  omega_matcher_set_chunk_size(m, 0);
+  return m;
+}
+
+omega_list_matcher_t *omega_list_matcher_create_from_buffer(const char *compiled_file, const uint8_t *patterns_buffer,
+                                                            uint64_t patterns_buffer_size, int case_insensitive,
+                                                            int ignore_punctuation, int elide_whitespace,
+                                                            omega_match_pattern_store_stats_t *stats) {
+  if (!patterns_buffer || patterns_buffer_size == 0) return nullptr;
+  if (omega_list_matcher_compile_patterns(compiled_file, patterns_buffer, patterns_buffer_size, case_insensitive,
+                                          ignore_punctuation, elide_whitespace, stats) != 0)
+    return nullptr;
+  return omega_list_matcher_create(compiled_file, case_insensitive, ignore_punctuation, elide_whitespace, stats);
+}
+
+int omega_list_matcher_add_stats(omega_list_matcher_t *m, omega_match_stats_t *stats) {
+  if (!m || !stats) return -1;
+  m->stats = stats;
+  return 0;
+}
+
+int omega_list_matcher_destroy(omega_list_matcher_t *m) {
+  if (!m) return -1;
+  delete m->engine;
+  if (m->file) olm::unmap(m->file, m->file_size);
+  if (m->temp_path) {
+    unlink(m->temp_path);
+    std::free(m->temp_path);
+  }
+  delete m;
+  return 0;
+}
+
+int omega_list_matcher_emit_header_info(const omega_list_matcher_t *m, FILE *fp) {
+  if (!m || !m->engine || !fp) return -1;
+  const olm::Header &h = m->engine->header();
+  std::fprintf(fp,
+               "Header v%d stats: total_patterns=%s, smallest_pattern_length=%s, largest_pattern_length=%s,"
+               " case_insensitive_support=%s, string_store_size=%s, bloom_filter_size=%s, num_occupied_buckets=%s,"
+               " table_size=%s, min_bucket_size=%s, max_bucket_size=%s, load_factor=%.2f, avg_bucket_size=%.2f\n",
+               int(h.version), with_commas(h.stored_patterns).c_str(), with_commas(h.smallest).c_str(),
+               with_commas(h.largest).c_str(), (h.flags & olm::kFlagIgnoreCase) ? "yes" : "no",
+               with_commas(h.store_bytes).c_str(), with_commas(h.bloom_bytes).c_str(),
+               with_commas(h.occupied).c_str(), with_commas(h.table_size).c_str(), with_commas(h.min_bucket).c_str(),
+               with_commas(h.max_bucket).c_str(), h.load_factor, h.avg_bucket);
+  return 0;
+}
+
+omega_match_results_t *omega_list_matcher_match(const omega_list_matcher_t *m, const uint8_t *haystack,
+                                                size_t haystack_size, int no_overlap, int longest_only,
+                                                int word_boundary, int word_prefix, int word_suffix, int line_start,
+                                                int line_end) {
+  if (!m || !m->engine) return nullptr;
+  omega_match_results_t *r = m->engine->match_host(
+      haystack, haystack_size,
+      to_flags(no_overlap, longest_only, word_boundary, word_prefix, word_suffix, line_start, line_end));
+  if (r && m->stats) m->engine->collect_stats(m->stats);
+  return r;
+}
+
+void omega_match_results_destroy(omega_match_results_t *results) {
+  if (!results) return;
+  std::free(results->matches);
+  results->matches = nullptr;
+  results->count = 0;
+  std::free(results);
+}
+
+int omega_matcher_set_num_threads(omega_list_matcher_t *m, int threads) {
+  if (!m) return -1;
+  const int mx = max_host_threads();
+  if (threads == 0) threads = mx;
+  else if (threads < 0 || threads > mx) return -1;
+  m->threads = threads;
+  return 0;
+}
+int omega_matcher_get_num_threads(const omega_list_matcher_t *m) { return m ? m->threads : -1; }
+
+int omega_matcher_set_chunk_size(omega_list_matcher_t *m, int chunk) {
+  if (!m) return -1;
+  if (chunk == 0) chunk = 4096;
+  else if (chunk < 1) return -1;
+  else if (chunk & (chunk - 1)) chunk = int(olm::next_pow2_u32(uint32_t(chunk)));
+  m->chunk = chunk;
+  return 0;
+}
+int omega_matcher_get_chunk_size(const omega_list_matcher_t *m) { return m ? m->chunk : -1; }
+
+/* ------------------------------------------------------------------ B200 extensions */
+
+int olm_cuda_set_default_device(int device) {
+  if (device < 0) return -1;
+  g_default_device = device;
+  return 0;
+}
+int olm_cuda_matcher_device(const omega_list_matcher_t *m) { return (m && m->engine) ? m->engine->device() : -1; }
+
+int olm_cuda_match_device(const omega_list_matcher_t *m, const void *dev_haystack, size_t n,
+                          const void *match_ptr_base, int no_overlap, int longest_only, int word_boundary,
+                          int word_prefix, int word_suffix, int line_start, int line_end, olm_cuda_results_t *out) {
+  if (!m || !m->engine || !out) return -1;
+  olm::ScanRange r;
+  r.dev = dev_haystack;
+  r.slice_begin = 0;
+  r.slice_len = n;
+  r.own_begin = 0;
+  r.own_end = n;
+  r.global_size = n;
+  r.match_ptr_base = reinterpret_cast<uint64_t>(match_ptr_base);
+  const int rc = m->engine->match_device(
+      r, to_flags(no_overlap, longest_only, word_boundary, word_prefix, word_suffix, line_start, line_end), out);
+  if (rc == 0 && m->stats) m->engine->collect_stats(m->stats);
+  return rc;
+}
+
+int olm_cuda_match_shard(const omega_list_matcher_t *m, const void *dev_slice, uint64_t slice_begin,
+                         uint64_t slice_len, uint64_t own_begin, uint64_t own_end, uint64_t global_size,
+                         const void *match_ptr_base, int longest_only, int word_boundary, int word_prefix,
+                         int word_suffix, int line_start, int line_end, olm_cuda_results_t *out) {
+  if (!m || !m->engine || !out) return -1;
+  olm::ScanRange r;
+  r.dev = dev_slice;
+  r.slice_begin = slice_begin;
+  r.slice_len = slice_len;
+  r.own_begin = own_begin;
+  r.own_end = own_end;
+  r.global_size = global_size;
+  r.match_ptr_base = reinterpret_cast<uint64_t>(match_ptr_base);
+  const int rc = m->engine->match_device(
+      r, to_flags(0, longest_only, word_boundary, word_prefix, word_suffix, line_start, line_end), out);
+  if (rc == 0 && m->stats) m->engine->collect_stats(m->stats);
+  return rc;
+}
+
+int64_t olm_cuda_no_overlap(const omega_list_matcher_t *m, void *dev_records, uint64_t count) {
+  if (!m || !m->engine) return -1;
+  return m->engine->no_overlap_inplace(dev_records, count);
+}
+
+int olm_cuda_sort_records(const omega_list_matcher_t *m, void *dev_records, uint64_t count) {
+  if (!m || !m->engine) return -1;
+  return m->engine->sort_records(dev_records, count);
+}
+
+int olm_cuda_last_timing(const omega_list_matcher_t *m, olm_cuda_timing_t *out) {
+  if (!m || !m->engine || !out) return -1;
+  *out = m->engine->timing();
+  return 0;
+}
+
+int olm_store_inspect(const char *compiled_file, olm_store_info_t *out) {
+  if (!compiled_file || !out) return -1;
+  size_t n = 0;
+  uint8_t *f = olm::map_whole_file(compiled_file, &n, false);
+  if (!f) return -1;
+  olm::StoreView v;
+  const std::string err = olm::parse_store(f, n, &v);
+  int rc = -1;
+  if (err.empty()) {
+    olm::StagedStore s;
+    olm::FilterBudget b;
+    const std::string e2 = olm::stage_store(v, b, &s);
+    if (e2.empty() && olm::check_staged_store(v, s) == 0) {
+      out->flags = v.hdr.flags;
+      out->smallest = v.hdr.smallest;
+      out->largest = v.hdr.largest;
+      out->stored_patterns = v.hdr.stored_patterns;
+      out->table_size = v.hdr.table_size;
+      out->occupied_buckets = v.hdr.occupied;
+      out->len1 = v.n1;
+      out->len2 = v.n2;
+      out->len3 = v.n3;
+      out->len4 = v.n4;
+      out->store_bytes = v.hdr.store_bytes;
+      out->file_bytes = n;
+      rc = 0;
+    } else {
+      std::fprintf(stderr, "libomega_match(b200): %s: %s\n", compiled_file, e2.empty() ? "self check failed" : e2.c_str());
+    }
+  } else {
+    std::fprintf(stderr, "libomega_match(b200): %s: %s\n", compiled_file, err.c_str());
+  }
+  olm::unmap(f, n);
+  return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,457 @@
+// engine.cu -- sequencing of one match call on one GPU.
+//
+//   no transform flag in the store (matcher.c:939-943):
+//       [memset descriptors] -> scan_kernel over the owned byte range -> (no_overlap filter)
+//   transform flag (matcher.c:945-1018): for every batch of <= kBatchWindows source windows
+//       transform (normalise, offset map, window descriptors) -> window tails -> scan_kernel
+//       over the normalised windows, the decoupled look-back continuing across batches so the
+//       records of all windows come out in one ordered array -> (no_overlap filter)
+//
+// The scan writes final records; the only host synchronisation of a call is the read-back of
+// the record count (needed to size the D2H copy / to detect a too small result buffer, in
+// which case the buffer is grown to the exact count and the call repeated).
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda_runtime.h>
+
+#include "filters.cuh"
+#include "scan.cuh"
+#include "transform.cuh"
+
+namespace olm {
+
+namespace {
+
+constexpr uint32_t kBatchWindows = 64;                 // 256 MiB of source per transform batch
+constexpr uint64_t kWinStride = kWindowBytes + 256;    // normalised windows are this far apart
+constexpr uint64_t kNormFront = 256;                   // readable bytes in front of window 0
+constexpr uint32_t kTilesPerWindow = kWindowBytes / kTileBytes;
+constexpr uint32_t kMaxBatches = 1u << 16;
+
+#define OLM_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      std::fprintf(stderr, "libomega_match(b200): %s failed: %s (%s:%d)\n", #expr,              \
+                   cudaGetErrorString(_e), __FILE__, __LINE__);                                 \
+      return -1;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n, bool keep = false) {
+    if (n <= cap) return 0;
+    size_t want = (n + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+    void *q = nullptr;
+    OLM_CUDA(cudaMalloc(&q, want));
+    if (keep && p && cap) OLM_CUDA(cudaMemcpy(q, p, cap, cudaMemcpyDeviceToDevice));
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+int upload(DevBuf &b, const std::vector<T> &v, const T **out) {
+  const size_t bytes = std::max<size_t>(16, v.size() * sizeof(T));
+  if (b.ensure(bytes)) return -1;
+  OLM_CUDA(cudaMemset(b.p, 0, bytes));
+  if (!v.empty()) OLM_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T *>(b.p);
+  return 0;
+}
+
+} // namespace
+
+struct EngineImpl {
+  int device = 0, sms = 0;
+  size_t smem_limit = 0;
+  cudaStream_t stream = nullptr;
+  Header hdr;
+  DeviceStore ds;
+  uint32_t stages = 0;
+  bool has_short_234 = false;
+  DevBuf d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
+  DevBuf hay, out, out2, tile_state, misc, norm, map, windows, ghost, fscratch;
+  cudaEvent_t ev[8] = {};
+  olm_cuda_timing_t last{};
+  uint64_t out_hint = 0;
+  unsigned long long counters[8] = {};
+  uint64_t attempts_last = 0;
+};
+
+Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string *err) {
+  auto fail = [&](const std::string &m) -> Engine * {
+    if (err) *err = m;
+    return nullptr;
+  };
+  StoreView view;
+  std::string e = parse_store(file, size, &view);
+  if (!e.empty()) return fail(e);
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: this library has no CPU matching path");
+  if (device < 0 || device >= ndev) return fail("CUDA device index out of range");
+  if (cudaSetDevice(device) != cudaSuccess) return fail("cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
+  if (prop.major < 10) return fail("this build contains sm_100a code only (needs a B200 class GPU)");
+
+  auto *impl = new EngineImpl();
+  Engine *eng = new Engine();
+  eng->impl_ = impl;
+  impl->device = device;
+  impl->sms = prop.multiProcessorCount;
+  impl->smem_limit = prop.sharedMemPerBlockOptin;
+  impl->hdr = view.hdr;
+
+  StagedStore staged;
+  FilterBudget budget;
+  const bool has_p23 = view.n1 || view.n2 || view.n3;
+  budget.g4_max_log2 = has_p23 ? 19 : 20;
+  budget.p23_max_log2 = 18;
+  e = stage_store(view, budget, &staged);
+  if (e.empty() && check_staged_store(view, staged) != 0) e = "internal error: staged store failed its self check";
+  if (!e.empty()) {
+    delete eng;
+    return fail(e);
+  }
+  impl->has_short_234 = view.n2 || view.n3 || view.n4;
+  impl->ds = staged.params;
+  bool ok = true;
+  ok = ok && upload(impl->d_slots, staged.slots, &impl->ds.slots) == 0;
+  ok = ok && upload(impl->d_recs, staged.recs, &impl->ds.recs) == 0;
+  ok = ok && upload(impl->d_store, staged.store, &impl->ds.store) == 0;
+  ok = ok && upload(impl->d_g4, staged.g4, &impl->ds.g4) == 0;
+  ok = ok && upload(impl->d_p23, staged.p23, &impl->ds.p23) == 0;
+  ok = ok && upload(impl->d_set3, staged.set3, &impl->ds.set3) == 0;
+  ok = ok && upload(impl->d_bitmap2, staged.bitmap2, &impl->ds.bitmap2) == 0;
+  ok = ok && cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+  ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
+  impl->stages = scan_pick_stages(impl->ds, impl->smem_limit);
+  if (!ok || impl->stages == 0) {
+    delete eng;
+    return fail("CUDA setup failed while uploading the store");
+  }
+  if (impl->hdr.flags & kFlagAnyTransform) {
+    ok = impl->ghost.ensure(kWindowBytes + 64) == 0 && cudaMemset(impl->ghost.p, 0, impl->ghost.cap) == cudaSuccess;
+    if (!ok) {
+      delete eng;
+      return fail("CUDA allocation failed");
+    }
+  }
+  return eng;
+}
+
+Engine::~Engine() {
+  if (!impl_) return;
+  cudaSetDevice(impl_->device);
+  for (DevBuf *b : {&impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->tile_state, &impl_->misc,
+                    &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch})
+    b->release();
+  for (auto &ev : impl_->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (impl_->stream) cudaStreamDestroy(impl_->stream);
+  delete impl_;
+}
+
+int Engine::device() const { return impl_->device; }
+const Header &Engine::header() const { return impl_->hdr; }
+const olm_cuda_timing_t &Engine::timing() const { return impl_->last; }
+
+int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_results_t *res) {
+  EngineImpl &E = *impl_;
+  OLM_CUDA(cudaSetDevice(E.device));
+  res->count = 0;
+  res->records = nullptr;
+  res->device = E.device;
+  E.last = olm_cuda_timing_t{};
+  std::memset(E.counters, 0, sizeof E.counters);
+  E.attempts_last = 0;
+
+  const bool windowed = E.hdr.flags & kFlagAnyTransform;
+  if (r.own_end < r.own_begin || r.own_end > r.global_size || r.own_begin < r.slice_begin ||
+      r.own_end > r.slice_begin + r.slice_len || (reinterpret_cast<uintptr_t>(r.dev) & 15) ||
+      ((r.own_begin - r.slice_begin) & 15)) {
+    std::fprintf(stderr, "libomega_match(b200): invalid scan range / unaligned device buffer\n");
+    return -1;
+  }
+  if (windowed && ((r.own_begin % kWindowBytes) != 0)) {
+    std::fprintf(stderr, "libomega_match(b200): shards of a transforming store must start on a 4 MiB window\n");
+    return -1;
+  }
+  const uint64_t n_own = r.own_end - r.own_begin;
+  if (n_own == 0) return 0;
+
+  // ---- plan
+  const uint64_t n_windows = windowed ? (n_own + kWindowBytes - 1) / kWindowBytes : 0;
+  const uint64_t tiles = windowed ? n_windows * kTilesPerWindow : (n_own + kTileBytes - 1) / kTileBytes;
+  const uint64_t n_batches = windowed ? (n_windows + kBatchWindows - 1) / kBatchWindows : 1;
+  if (tiles >= 0xFFFFFFF0ull || n_batches > kMaxBatches) {
+    std::fprintf(stderr, "libomega_match(b200): haystack too large for one call\n");
+    return -1;
+  }
+  if (E.tile_state.ensure((tiles + 1) * 8)) return -1;
+  // misc: [0..n_batches) u32 tickets | @ 256 KiB: total (u64), filter total (u64), counters[8]
+  const size_t misc_total_off = size_t(kMaxBatches) * 4;
+  if (E.misc.ensure(misc_total_off + 256)) return -1;
+  unsigned int *d_tickets = static_cast<unsigned int *>(E.misc.p);
+  unsigned long long *d_total = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + misc_total_off);
+  unsigned long long *d_ftotal = d_total + 1;
+  unsigned long long *d_counters = d_total + 2;
+
+  const bool identity_map = windowed && !(E.hdr.flags & (kFlagIgnorePunct | kFlagElideSpace));
+  if (windowed) {
+    const uint64_t bw = std::min<uint64_t>(n_windows, kBatchWindows);
+    if (E.norm.ensure(kNormFront + bw * kWinStride + 256)) return -1;
+    if (!identity_map && E.map.ensure(bw * uint64_t(kWindowBytes) * 4)) return -1;
+    if (E.windows.ensure(n_windows * sizeof(WindowDesc))) return -1;
+  }
+
+  uint64_t cap = std::max<uint64_t>(E.out_hint, n_own / 64 + 4096);
+  if (E.out.cap / sizeof(Record) >= cap) cap = E.out.cap / sizeof(Record);
+
+  uint32_t fl = 0;
+  if (f.word_boundary) fl |= kWordBoundary;
+  if (f.word_prefix) fl |= kWordPrefix;
+  if (f.word_suffix) fl |= kWordSuffix;
+  if (f.line_start) fl |= kLineStart;
+  if (f.line_end) fl |= kLineEnd;
+  if (f.longest_only) fl |= kLongestOnly;
+  if (windowed) fl |= kWindowMode;
+  if (identity_map) fl |= kIdentityMap;
+
+  unsigned long long total = 0;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    if (E.out.ensure(cap * sizeof(Record))) return -1;
+    cap = E.out.cap / sizeof(Record);
+    OLM_CUDA(cudaMemsetAsync(E.tile_state.p, 0, (tiles + 1) * 8, E.stream));
+    OLM_CUDA(cudaMemsetAsync(E.misc.p, 0, n_batches * 4, E.stream));
+    OLM_CUDA(cudaMemsetAsync(d_total, 0, 128, E.stream));
+    uint32_t launches = 0, scan_launches = 0;
+    OLM_CUDA(cudaEventRecord(E.ev[0], E.stream));
+
+    ScanParams P{};
+    P.st = E.ds;
+    P.tile_state = static_cast<unsigned long long *>(E.tile_state.p);
+    P.out = static_cast<Record *>(E.out.p);
+    P.out_cap = cap;
+    P.match_ptr_base = r.match_ptr_base;
+    P.total = d_total;
+    P.counters = d_counters;
+    P.flags = fl;
+    P.stages = E.stages;
+    P.tail_byte = 0;
+
+    if (!windowed) {
+      P.buf = static_cast<const uint8_t *>(r.dev);
+      P.buf_len = (r.slice_len + 15) & ~uint64_t(15);
+      P.seg_buf_off = -(int64_t)r.slice_begin;
+      P.seg_len = r.global_size;
+      P.scan_begin = r.own_begin;
+      P.scan_end = r.own_end;
+      P.num_tiles = (uint32_t)tiles;
+      P.tile_base = 0;
+      P.ticket = d_tickets;
+      const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)E.sms);
+      OLM_CUDA(scan_launch(P, grid, E.stream));
+      ++launches;
+      ++scan_launches;
+    } else {
+      float tf_ms = 0.f;
+      (void)tf_ms;
+      for (uint64_t b = 0; b < n_batches; ++b) {
+        const uint64_t w0 = b * kBatchWindows;
+        const uint32_t nw = (uint32_t)std::min<uint64_t>(kBatchWindows, n_windows - w0);
+        TransformParams T{};
+        T.src = static_cast<const uint8_t *>(r.dev);
+        T.src_off = (r.own_begin - r.slice_begin) + w0 * kWindowBytes;
+        T.src_len = std::min<uint64_t>(uint64_t(nw) * kWindowBytes, n_own - w0 * kWindowBytes);
+        T.norm = static_cast<uint8_t *>(E.norm.p);
+        T.norm_off = kNormFront;
+        T.win_stride = kWinStride;
+        T.map = identity_map ? nullptr : static_cast<uint32_t *>(E.map.p);
+        T.windows = static_cast<WindowDesc *>(E.windows.p) + w0;
+        T.ghost = static_cast<uint8_t *>(E.ghost.p);
+        T.flags = E.hdr.flags;
+        OLM_CUDA(transform_launch(T, nw, E.has_short_234, E.sms, E.stream, &launches));
+
+        P.buf = static_cast<const uint8_t *>(E.norm.p);
+        P.buf_len = E.norm.cap & ~size_t(15);
+        P.windows = T.windows;
+        P.map = T.map;
+        P.win_stride = kWinStride;
+        P.win_buf_off = kNormFront;
+        P.win_src_base = r.own_begin + w0 * kWindowBytes;
+        P.tiles_per_win = kTilesPerWindow;
+        P.num_tiles = nw * kTilesPerWindow;
+        P.tile_base = (uint32_t)(w0 * kTilesPerWindow);
+        P.ticket = d_tickets + b;
+        const int grid = (int)std::min<uint64_t>(P.num_tiles, (uint64_t)E.sms);
+        OLM_CUDA(scan_launch(P, grid, E.stream));
+        ++launches;
+        ++scan_launches;
+      }
+    }
+    OLM_CUDA(cudaEventRecord(E.ev[1], E.stream));
+    OLM_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, E.stream));
+    OLM_CUDA(cudaMemcpyAsync(E.counters, d_counters, sizeof E.counters, cudaMemcpyDeviceToHost, E.stream));
+    OLM_CUDA(cudaStreamSynchronize(E.stream));
+    E.last.kernel_launches = launches;
+    E.last.scan_launches = scan_launches;
+    if (total <= cap) break;
+    if (attempt == 2) {
+      std::fprintf(stderr, "libomega_match(b200): result buffer still too small after retry\n");
+      return -1;
+    }
+    cap = total + total / 16 + 4096; // exact count is known now
+  }
+  E.out_hint = std::max<uint64_t>(E.out_hint, total + total / 8);
+  E.last.matches_before_filter = total;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, E.ev[0], E.ev[1]);
+  E.last.scan_ms = ms;
+  E.last.total_ms = ms;
+
+  void *final_records = E.out.p;
+  if (f.no_overlap && total > 1) {
+    if (E.out2.ensure(total * sizeof(Record))) return -1;
+    if (E.fscratch.ensure(filter_scratch_bytes(total))) return -1;
+    uint32_t launches = 0;
+    OLM_CUDA(cudaEventRecord(E.ev[2], E.stream));
+    OLM_CUDA(no_overlap_launch(static_cast<const Record *>(E.out.p), total, static_cast<Record *>(E.out2.p),
+                               E.fscratch.p, d_ftotal, E.stream, &launches));
+    OLM_CUDA(cudaEventRecord(E.ev[3], E.stream));
+    OLM_CUDA(cudaMemcpyAsync(&total, d_ftotal, sizeof total, cudaMemcpyDeviceToHost, E.stream));
+    OLM_CUDA(cudaStreamSynchronize(E.stream));
+    cudaEventElapsedTime(&ms, E.ev[2], E.ev[3]);
+    E.last.filter_ms = ms;
+    E.last.total_ms += ms;
+    E.last.kernel_launches += launches;
+    std::swap(E.out, E.out2);
+    final_records = E.out.p;
+  }
+  // statistics that do not need a kernel: long-path attempts without word_boundary
+  if (E.hdr.largest >= 5 && !f.word_boundary && !windowed) {
+    const uint64_t lim = r.global_size >= 3 ? r.global_size - 3 : 0;
+    const uint64_t hi = std::min<uint64_t>(r.own_end, lim);
+    E.attempts_last = hi > r.own_begin ? hi - r.own_begin : 0;
+  }
+  res->count = total;
+  res->records = final_records;
+  return 0;
+}
+
+omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, const MatchFlags &f) {
+  EngineImpl &E = *impl_;
+  auto *results = static_cast<omega_match_results_t *>(std::malloc(sizeof(omega_match_results_t)));
+  if (!results) return nullptr;
+  results->count = 0;
+  results->matches = static_cast<omega_match_result_t *>(std::malloc(sizeof(omega_match_result_t)));
+  if (n == 0 || !haystack) return results;
+  auto bail = [&]() -> omega_match_results_t * {
+    std::free(results->matches);
+    std::free(results);
+    return nullptr;
+  };
+  if (cudaSetDevice(E.device) != cudaSuccess) return bail();
+  const size_t padded = ((n + 15) & ~size_t(15)) + 256;
+  if (E.hay.ensure(padded)) return bail();
+  cudaEventRecord(E.ev[4], E.stream);
+  if (cudaMemcpyAsync(E.hay.p, haystack, n, cudaMemcpyHostToDevice, E.stream) != cudaSuccess) return bail();
+  cudaEventRecord(E.ev[5], E.stream);
+  ScanRange r;
+  r.dev = E.hay.p;
+  r.slice_begin = 0;
+  r.slice_len = n;
+  r.own_begin = 0;
+  r.own_end = n;
+  r.global_size = n;
+  r.match_ptr_base = reinterpret_cast<uint64_t>(haystack);
+  olm_cuda_results_t dres;
+  if (match_device(r, f, &dres) != 0) return bail();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, E.ev[4], E.ev[5]);
+  E.last.h2d_ms = ms;
+  if (dres.count) {
+    std::free(results->matches);
+    results->matches = static_cast<omega_match_result_t *>(std::malloc(dres.count * sizeof(omega_match_result_t)));
+    if (!results->matches) {
+      std::free(results);
+      return nullptr;
+    }
+    cudaEventRecord(E.ev[6], E.stream);
+    if (cudaMemcpyAsync(results->matches, dres.records, dres.count * sizeof(Record), cudaMemcpyDeviceToHost,
+                        E.stream) != cudaSuccess)
+      return bail();
+    cudaEventRecord(E.ev[7], E.stream);
+    if (cudaStreamSynchronize(E.stream) != cudaSuccess) return bail();
+    cudaEventElapsedTime(&ms, E.ev[6], E.ev[7]);
+    E.last.d2h_ms = ms;
+  }
+  results->count = dres.count;
+  return results;
+}
+
+int64_t Engine::no_overlap_inplace(void *dev_records, uint64_t count) {
+  EngineImpl &E = *impl_;
+  OLM_CUDA(cudaSetDevice(E.device));
+  if (count < 2) return (int64_t)count;
+  if (E.out2.ensure(count * sizeof(Record))) return -1;
+  if (E.fscratch.ensure(filter_scratch_bytes(count))) return -1;
+  if (E.misc.ensure(size_t(kMaxBatches) * 4 + 256)) return -1;
+  unsigned long long *d_ftotal =
+      reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + size_t(kMaxBatches) * 4) + 1;
+  uint32_t launches = 0;
+  unsigned long long total = 0;
+  OLM_CUDA(no_overlap_launch(static_cast<const Record *>(dev_records), count, static_cast<Record *>(E.out2.p),
+                             E.fscratch.p, d_ftotal, E.stream, &launches));
+  OLM_CUDA(cudaMemcpyAsync(&total, d_ftotal, sizeof total, cudaMemcpyDeviceToHost, E.stream));
+  OLM_CUDA(cudaStreamSynchronize(E.stream));
+  OLM_CUDA(cudaMemcpyAsync(dev_records, E.out2.p, total * sizeof(Record), cudaMemcpyDeviceToDevice, E.stream));
+  OLM_CUDA(cudaStreamSynchronize(E.stream));
+  return (int64_t)total;
+}
+
+int Engine::sort_records(void *dev_records, uint64_t count) {
+  EngineImpl &E = *impl_;
+  OLM_CUDA(cudaSetDevice(E.device));
+  if (count < 2) return 0;
+  if (E.out2.ensure(count * sizeof(Record))) return -1;
+  if (E.fscratch.ensure(sort_scratch_bytes(count))) return -1;
+  uint32_t launches = 0;
+  OLM_CUDA(sort_records_launch(static_cast<Record *>(dev_records), static_cast<Record *>(E.out2.p), count,
+                               E.fscratch.p, E.stream, &launches));
+  OLM_CUDA(cudaStreamSynchronize(E.stream));
+  return 0;
+}
+
+void Engine::collect_stats(omega_match_stats_t *s) {
+  if (!s) return;
+  const EngineImpl &E = *impl_;
+  // counters written by the scan: [0] hits  [1] misses  [2] comparisons
+  s->total_hits += E.counters[0];
+  s->total_misses += E.counters[1];
+  s->total_comparisons += E.counters[2];
+  s->total_attempts += E.attempts_last;
+  const uint64_t long_hits = E.counters[3];
+  s->total_filtered += E.attempts_last > long_hits ? E.attempts_last - long_hits : 0;
+}
+
+} // namespace olm

@@ -1,0 +1,55 @@
+// engine.h -- one matcher on one GPU: the uploaded store, work buffers, and the sequence of
+// kernels that make up a match call.  Plain C++ interface; api.cpp puts the C ABI on top.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "../../include/olm_b200.h"
+#include "store.h"
+
+namespace olm {
+
+struct MatchFlags {
+  bool no_overlap = false, longest_only = false, word_boundary = false, word_prefix = false,
+       word_suffix = false, line_start = false, line_end = false;
+};
+
+// What part of which haystack a call scans.
+struct ScanRange {
+  const void *dev = nullptr;   // device bytes of [slice_begin, slice_begin + slice_len)
+  uint64_t slice_begin = 0, slice_len = 0;
+  uint64_t own_begin = 0, own_end = 0; // start positions reported by this call
+  uint64_t global_size = 0;
+  uint64_t match_ptr_base = 0;
+};
+
+struct EngineImpl;
+
+class Engine {
+public:
+  // Parses + re-stages the mapped store and uploads it.  On failure returns nullptr and
+  // fills *err.
+  static Engine *create(const uint8_t *file, size_t size, int device, std::string *err);
+  ~Engine();
+
+  int device() const;
+  const Header &header() const;
+
+  // Device-resident input, device-resident output (records stay in the engine's buffer).
+  int match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_results_t *out);
+  // Host input/output: H2D, match_device, D2H into a malloc'ed array.
+  omega_match_results_t *match_host(const uint8_t *haystack, size_t n, const MatchFlags &f);
+
+  int64_t no_overlap_inplace(void *dev_records, uint64_t count);
+  int sort_records(void *dev_records, uint64_t count);
+
+  const olm_cuda_timing_t &timing() const;
+  void collect_stats(omega_match_stats_t *accum); // adds the counters of the last call
+
+private:
+  Engine() = default;
+  EngineImpl *impl_ = nullptr;
+};
+
+} // namespace olm

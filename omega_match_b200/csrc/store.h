@@ -1,0 +1,62 @@
+// store.h -- host view of a compiled store and the builder of its HBM layout.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "device_tables.h"
+#include "olm_format.h"
+
+namespace olm {
+
+// Parsed (not copied) view of a mapped .olm file.  Reference reader: matcher.c:329-432.
+struct StoreView {
+  const uint8_t *base = nullptr;
+  size_t size = 0;
+  Header hdr;
+  const uint8_t *patterns = nullptr; // hdr.store_bytes
+  uint32_t bloom_bits = 0;
+  const uint8_t *bloom = nullptr; // hdr.bloom_bytes
+  const uint8_t *index = nullptr; // hdr.table_size * 4
+  const uint8_t *blob = nullptr;  // hdr.blob_bytes
+  const uint8_t *bitmap1 = nullptr, *bitmap2 = nullptr;
+  uint32_t n1 = 0, n2 = 0, n3 = 0, n4 = 0;
+  const uint8_t *arr3 = nullptr, *arr4 = nullptr;
+};
+
+// Returns an empty string on success, else what is wrong with the file.
+std::string parse_store(const uint8_t *file, size_t size, StoreView *out);
+
+// Host-side image of the device tables (device_tables.h), ready to be uploaded verbatim.
+struct StagedStore {
+  std::vector<Slot> slots;
+  std::vector<Rec> recs;
+  std::vector<uint8_t> store;
+  std::vector<uint32_t> g4, p23, set3, bitmap2;
+  DeviceStore params; // pointer members are filled in after upload
+  uint32_t n_keys = 0;
+};
+
+// Limits for the two shared-memory filters, in log2(bits).
+struct FilterBudget {
+  uint32_t g4_max_log2 = 20;  // 128 KiB
+  uint32_t p23_max_log2 = 18; // 32 KiB
+};
+
+std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedStore *out);
+
+// Walks every pattern of the file through the staged tables exactly as the scan kernel would
+// probe them; returns the number of patterns that are NOT reachable (0 = tables are sound).
+// Used by CPU-only tests; it does not match haystacks.
+uint64_t check_staged_store(const StoreView &v, const StagedStore &s);
+
+// host mirror of the device hashing (scan.cu uses the same expressions)
+inline uint32_t slot_home(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.slot_shift; }
+inline uint32_t g4_bit(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.g4_shift; }
+inline uint32_t p23_bit(const DeviceStore &d, uint32_t gram) {
+  return ((gram & d.p23_and) * d.p23_mul) >> d.p23_shift;
+}
+inline uint32_t set3_home(const DeviceStore &d, uint32_t key3) { return (key3 * kHashMul >> 8) & d.set3_mask; }
+
+} // namespace olm

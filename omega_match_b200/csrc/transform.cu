@@ -1,0 +1,275 @@
+// transform.cu -- haystack normalisation for stores compiled with a transform flag
+// (kernel K2 of SURVEY 2.1).
+//
+// Reference: the serial window loop of omega_list_matcher_match (omega_match/src/matcher.c:
+// 945-1010) calling transform_apply (transform_table.c:36-88) once per 4 MiB SOURCE window.
+// Semantics reproduced exactly:
+//   * windows are independent: the "inside a whitespace run" state restarts at every window;
+//   * with elide-whitespace a whitespace byte is emitted (as ' ') iff the previous NON-SKIPPED
+//     byte of the window is not whitespace -- the run looks through removed punctuation;
+//   * after the window one trailing ' ' is dropped from the length (the byte stays in the
+//     buffer: `extent` = length + 1) -- also when the space is a literal one of a
+//     case-folding-only store;
+//   * `tail` = the byte the reference's unguarded short-matcher test reads at index M_w of
+//     its re-used scratch buffer: ' ' after a trim, else whatever an earlier window (of this
+//     call or a previous one) left there -- kept in `ghost`, a 4 MiB + 1 image of that buffer.
+//
+// One CTA normalises one window.  Per 16 KiB block: 16 bytes per thread, classification, a
+// "last non-skipped byte was whitespace" carry resolved with ballots, an exclusive block scan
+// of the kept-byte counts, and scattered stores of the kept bytes and of their source
+// indices (the transformed->original offset map).
+#include "transform.cuh"
+
+#include "olm_classes.h"
+
+namespace olm {
+
+namespace {
+
+constexpr int kTfThreads = 1024;
+constexpr int kTfWarps = kTfThreads / 32;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(kTfThreads, 1) transform_kernel(TransformParams P) {
+  __shared__ uint32_t s_cnt[kTfWarps];   // kept bytes per warp
+  __shared__ uint32_t s_has[kTfWarps];   // warp saw a non-skipped byte
+  __shared__ uint32_t s_last[kTfWarps];  // ... and the last one was whitespace
+  __shared__ uint32_t s_total;
+
+  const uint32_t win = blockIdx.x;
+  const uint64_t src_base = P.src_off + (uint64_t)win * kWindowBytes;
+  const uint64_t remain = P.src_len - (uint64_t)win * kWindowBytes;
+  const uint32_t wlen = remain < kWindowBytes ? (uint32_t)remain : kWindowBytes;
+  const uint8_t *src = P.src + src_base;
+  uint8_t *out = P.norm + P.norm_off + (uint64_t)win * P.win_stride;
+  uint32_t *map = P.map ? P.map + (uint64_t)win * kWindowBytes : nullptr;
+  const bool ci = P.flags & kFlagIgnoreCase, ip = P.flags & kFlagIgnorePunct, ew = P.flags & kFlagElideSpace;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t out_base = 0;    // bytes emitted by earlier blocks of this window
+  uint32_t carry_space = 0; // transform_table.c:54  in_space = 0 at the start of every window
+
+  for (uint32_t blk = 0; blk < wlen; blk += kTfThreads * 16) {
+    const uint32_t i0 = blk + tid * 16;
+    uint32_t bytes[4] = {0, 0, 0, 0};
+    uint32_t nvalid = 0;
+    if (i0 < wlen) {
+      nvalid = wlen - i0 < 16 ? wlen - i0 : 16;
+      if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(src + i0) & 15) == 0)) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + i0));
+        bytes[0] = v.x; bytes[1] = v.y; bytes[2] = v.z; bytes[3] = v.w;
+      } else {
+        for (uint32_t k = 0; k < nvalid; ++k) bytes[k >> 2] |= (uint32_t)src[i0 + k] << (8 * (k & 3));
+      }
+    }
+    // classify; per thread: does it contain a non-skipped byte, and is the last one a space
+    uint32_t act_space = 0, act_skip = 0; // bit k set: byte k is whitespace-class / skipped
+    uint32_t mapped[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t c = (bytes[k >> 2] >> (8 * (k & 3))) & 0xFF;
+      uint32_t m;
+      const ByteAction a = classify_byte(c, ci, ip, ew, &m);
+      if ((uint32_t)k < nvalid) {
+        if (a == kSpace) act_space |= 1u << k;
+        if (a == kSkip) act_skip |= 1u << k;
+      } else {
+        act_skip |= 1u << k;
+      }
+      mapped[k >> 2] |= m << (8 * (k & 3));
+    }
+    const uint32_t nonskip = ~act_skip & 0xFFFFu;
+    const uint32_t t_has = nonskip != 0;
+    const uint32_t t_last = t_has ? ((act_space >> (31 - __clz(nonskip))) & 1u) : 0u;
+
+    // carry-in of this thread: state after the nearest earlier thread that has a non-skipped byte
+    const uint32_t bal_has = __ballot_sync(kFull, t_has);
+    const uint32_t bal_last = __ballot_sync(kFull, t_last);
+    if (lane == 0) {
+      s_has[warp] = bal_has != 0;
+      s_last[warp] = bal_has ? ((bal_last >> (31 - __clz(bal_has))) & 1u) : 0u;
+    }
+    __syncthreads();
+    uint32_t warp_in = carry_space;
+    {
+      const uint32_t wh = __ballot_sync(kFull, s_has[lane]);
+      const uint32_t wl = __ballot_sync(kFull, s_last[lane]);
+      const uint32_t before = wh & ((1u << warp) - 1u);
+      if (before) warp_in = (wl >> (31 - __clz(before))) & 1u;
+      // state after the whole block, for the next iteration
+      if (wh) carry_space = (wl >> (31 - __clz(wh))) & 1u;
+    }
+    uint32_t in_space = warp_in;
+    {
+      const uint32_t before = bal_has & ((1u << lane) - 1u);
+      if (before) in_space = (bal_last >> (31 - __clz(before))) & 1u;
+    }
+    // keep mask (transform_table.c:56-78)
+    uint32_t keep = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t bit = 1u << k;
+      if (act_skip & bit) continue;
+      if (act_space & bit) {
+        if (!in_space) keep |= bit;
+        in_space = 1;
+      } else {
+        keep |= bit;
+        in_space = 0;
+      }
+    }
+    const uint32_t cnt = __popc(keep);
+    // block exclusive scan of cnt
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) s_cnt[warp] = incl;
+    __syncthreads();
+    uint32_t wsum = s_cnt[lane], wincl = wsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, wincl, d);
+      if (lane >= (uint32_t)d) wincl += t;
+    }
+    const uint32_t warp_excl = __shfl_sync(kFull, wincl - wsum, warp);
+    const uint32_t block_total = __shfl_sync(kFull, wincl, 31);
+    uint32_t o = out_base + warp_excl + (incl - cnt);
+    // scatter kept bytes and their source indices
+    uint32_t kk = keep;
+    while (kk) {
+      const uint32_t k = __ffs(kk) - 1;
+      kk &= kk - 1;
+      out[o] = (uint8_t)(mapped[k >> 2] >> (8 * (k & 3)));
+      if (map) map[o] = i0 + k;
+      ++o;
+    }
+    out_base += block_total;
+    __syncthreads(); // s_* are rewritten by the next block
+  }
+
+  // trailing-space trim (transform_table.c:82-84) and the window descriptor
+  __threadfence_block();
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t m = out_base, extent = out_base;
+    if (m > 0 && out[m - 1] == ' ') --m;
+    WindowDesc d;
+    d.norm_len = m;
+    d.extent = extent;
+    d.tail = (m != extent) ? (uint32_t)' ' : 0xFFFFFFFFu; // resolved by window_tails_kernel
+    d._pad = 0;
+    P.windows[win] = d;
+  }
+}
+
+// tail(w) for windows that were not trimmed: the byte at index M_w left behind by the most
+// recent earlier window whose written extent exceeds M_w, else the ghost image.
+__global__ void window_tails_kernel(TransformParams P, uint32_t n_windows) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (uint32_t w = 0; w < n_windows; ++w) {
+    WindowDesc d = P.windows[w];
+    if (d.tail != 0xFFFFFFFFu) continue;
+    const uint32_t m = d.norm_len;
+    uint32_t t = P.ghost[m];
+    for (uint32_t v = w; v-- > 0;) {
+      if (P.windows[v].extent > m) {
+        t = P.norm[P.norm_off + (uint64_t)v * P.win_stride + m];
+        break;
+      }
+    }
+    P.windows[w].tail = t;
+  }
+}
+
+// ghost[i] <- byte i of the last window of this batch whose extent exceeds i (older content
+// survives elsewhere), i.e. the state of the reference's scratch buffer after these windows.
+__global__ void ghost_update_kernel(TransformParams P, uint32_t n_windows) {
+  const uint32_t span = (kWindowBytes + gridDim.x) / gridDim.x;
+  const uint32_t lo = blockIdx.x * span;
+  uint32_t hi = lo + span;
+  if (hi > kWindowBytes + 1) hi = kWindowBytes + 1;
+  // walk the windows from last to first; `done_to` = indices below it are final
+  uint32_t done_to = lo;
+  for (uint32_t v = n_windows; v-- > 0 && done_to < hi;) {
+    uint32_t ext = P.windows[v].extent;
+    if (ext > hi) ext = hi;
+    if (ext > done_to) {
+      const uint8_t *srcw = P.norm + P.norm_off + (uint64_t)v * P.win_stride;
+      for (uint32_t i = done_to + threadIdx.x; i < ext; i += blockDim.x) P.ghost[i] = srcw[i];
+      done_to = ext;
+    }
+  }
+}
+
+// Case folding only: no compaction, identity offset map.  Streams the whole batch at once.
+__global__ void fold_case_kernel(TransformParams P, uint32_t n_windows) {
+  const uint64_t total = P.src_len;
+  const uint64_t n16 = (total + 15) / 16;
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n16;
+       v += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = v * 16;
+    const uint32_t win = (uint32_t)(i / kWindowBytes);
+    const uint32_t wi = (uint32_t)(i % kWindowBytes);
+    const uint8_t *s = P.src + P.src_off + i;
+    uint8_t *o = P.norm + P.norm_off + (uint64_t)win * P.win_stride + wi;
+    uint32_t w[4];
+    const uint32_t nvalid = total - i < 16 ? (uint32_t)(total - i) : 16;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(s) & 15) == 0)) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(s));
+      w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+    } else {
+      w[0] = w[1] = w[2] = w[3] = 0;
+      for (uint32_t k = 0; k < nvalid; ++k) w[k >> 2] |= (uint32_t)s[k] << (8 * (k & 3));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // SWAR: bytes in 'a'..'z' get bit 5 cleared
+      const uint32_t x = w[j];
+      const uint32_t hi7 = x & 0x7F7F7F7Fu;
+      const uint32_t ge_a = hi7 + 0x1F1F1F1Fu;          // bit7 set iff (x&0x7f) >= 'a' (0x61)
+      const uint32_t gt_z = hi7 + 0x05050505u;          // bit7 set iff (x&0x7f) >  'z' (0x7a)
+      const uint32_t is_lower = ge_a & ~gt_z & ~x & 0x80808080u;
+      w[j] = x ^ (is_lower >> 2);
+    }
+    *reinterpret_cast<uint4 *>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // descriptors: one thread per window
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid < n_windows) {
+    const uint64_t remain = total - (uint64_t)gtid * kWindowBytes;
+    const uint32_t wlen = remain < kWindowBytes ? (uint32_t)remain : kWindowBytes;
+    const uint8_t last = P.src[P.src_off + (uint64_t)gtid * kWindowBytes + wlen - 1];
+    WindowDesc d;
+    d.extent = wlen;
+    d.norm_len = (last == ' ') ? wlen - 1 : wlen;
+    d.tail = (last == ' ') ? (uint32_t)' ' : 0xFFFFFFFFu;
+    d._pad = 0;
+    P.windows[gtid] = d;
+  }
+}
+
+} // namespace
+
+cudaError_t transform_launch(const TransformParams &p, uint32_t n_windows, bool need_tails, int sms,
+                             cudaStream_t stream, uint32_t *launches) {
+  if (n_windows == 0) return cudaSuccess;
+  const bool fold_only = (p.flags & kFlagAnyTransform) == kFlagIgnoreCase;
+  if (fold_only) {
+    fold_case_kernel<<<sms * 4, 512, 0, stream>>>(p, n_windows);
+  } else {
+    transform_kernel<<<n_windows, kTfThreads, 0, stream>>>(p);
+  }
+  ++*launches;
+  window_tails_kernel<<<1, 32, 0, stream>>>(p, n_windows);
+  ++*launches;
+  if (need_tails) {
+    ghost_update_kernel<<<sms, 256, 0, stream>>>(p, n_windows);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}
+
+} // namespace olm
