@@ -4,7 +4,10 @@
 // slots, so nothing of the file is used in place.  At create() the store is
 // re-staged into:
 //
-//   slots[]   one 16-byte record per distinct gram, open addressing, load <= 0.5.  Holds
+//   slots[]   one 16-byte record per distinct gram in BUCKETS of two (one 32-byte sector):
+//             a gram lives in the first bucket, counted from its home bucket, that had a free
+//             slot when it was inserted; a probe stops at the first bucket with a free slot.
+//             Load <= 0.5, so most probes -- hit or miss -- cost one sector.  A slot holds
 //             everything the scan needs to REJECT a candidate with one 16-byte load: the
 //             gram, pattern bytes 4..7 and the length of the (longest) pattern.  Grams of
 //             4-byte patterns live in the same table (flag bit) -> the length-4 short matcher
@@ -52,8 +55,8 @@ struct DeviceStore {
   const uint32_t *set3 = nullptr;    // open addressing, value = key3 + 1, 0 = empty
   const uint32_t *bitmap2 = nullptr; // 2048 words, bit (b0<<8|b1) as in short_matcher_t
   uint32_t bitmap1[8] = {0};         // bit b as in short_matcher_t
-  uint32_t slot_shift = 32;          // slot index = (gram*kHashMul) >> slot_shift
-  uint32_t slot_mask = 0;
+  uint32_t slot_shift = 32;          // home BUCKET = (gram*kHashMul) >> slot_shift; slots 2b, 2b+1
+  uint32_t slot_mask = 0;            // number of buckets - 1
   uint32_t g4_shift = 32, g4_words = 0;
   uint32_t p23_and = 0, p23_mul = 1, p23_shift = 32, p23_words = 0;
   uint32_t set3_mask = 0;

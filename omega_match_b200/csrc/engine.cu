@@ -82,7 +82,7 @@ struct EngineImpl {
   cudaStream_t stream = nullptr;
   Header hdr;
   DeviceStore ds;
-  uint32_t stages = 0;
+  uint32_t stages = 0, stage_cap = 0;
   bool has_short_234 = false;
   DevBuf d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
   DevBuf hay, out, out2, tile_state, misc, norm, map, windows, ghost, fscratch;
@@ -143,7 +143,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
   ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
-  impl->stages = scan_pick_stages(impl->ds, impl->smem_limit);
+  impl->stages = scan_pick_stages(impl->ds, impl->smem_limit, &impl->stage_cap);
   if (!ok || impl->stages == 0) {
     delete eng;
     return fail("CUDA setup failed while uploading the store");
@@ -257,6 +257,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.counters = d_counters;
     P.flags = fl;
     P.stages = E.stages;
+    P.stage_cap = E.stage_cap;
     P.tail_byte = 0;
 
     if (!windowed) {

@@ -95,6 +95,9 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 __device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
   asm volatile("st.global.release.gpu.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// 16-byte slot load through the read-only path.  (ld.global.nc.L1::no_allocate was tried: the
+// 32 MiB table of the 1M-pattern store then stopped being retained by L2 -- hit rate 95% -> 25%,
+// 61 GB of DRAM reads per GiB scanned, profiles/r1_notes.md -- so the default policy stays.)
 __device__ __forceinline__ uint4 ldg_slot(const Slot *p) {
   return __ldg(reinterpret_cast<const uint4 *>(p));
 }
@@ -125,6 +128,7 @@ struct Scanner {
   // hits = buckets found + short matches accepted, misses = short candidates rejected by a
   // predicate, comparisons = bucket patterns that fit (matcher.c:783-799, :818-877, :210)
   mutable uint32_t n_hits = 0, n_miss = 0, n_cmp = 0, n_long_hits = 0;
+  mutable uint32_t stat_inc = 1; // 0 while a position is evaluated a second time
 
   __device__ __forceinline__ uint32_t hay_byte(const TileCtx &T, unsigned long long pos) const {
     const unsigned long long rel = pos - T.p0;
@@ -168,39 +172,82 @@ struct Scanner {
     return true;
   }
 
-  // Everything the reference does for ONE position (matcher.c:769-880); `emit(len)` is
-  // called once per accepted match, longest first.
+  // ---- one candidate position, split in two so that several probes can be in flight ----
+  // probe_issue : position predicates (matcher.c:770-776, :195-196, :806-807), the gram, and
+  //               the loads of the candidate's home bucket (two 16-byte slots = one sector);
+  // probe_finish: everything else the reference does for the position (matcher.c:782-880);
+  //               `emit(len)` is called once per accepted match, longest first.
+  struct Probe {
+    uint32_t tpos, gram, bucket, flags; // flags: 1 = alive, 2 = gram candidate (and >= 4 bytes left), 4 = short candidate
+    uint4 a, b;
+  };
+
+  __device__ __forceinline__ void probe_issue(const TileCtx &T, bool valid, uint32_t tpos, bool cand_g, bool cand_p,
+                                              Probe &pr) const {
+    pr.tpos = tpos;
+    pr.flags = 0;
+    pr.gram = 0;
+    pr.bucket = 0;
+    pr.a = make_uint4(0, 0, 0, 0);
+    pr.b = make_uint4(0, 0, 0, 0);
+    if (!valid) return;
+    const unsigned long long pos = T.p0 + tpos;
+    const uint8_t *q = T.sb + kTilePre + tpos;
+    if (fl & (kWordBoundary | kWordPrefix | kLineStart)) {
+      const uint32_t prev = q[-1];
+      if (fl & kWordBoundary) { // matcher.c:770-776
+        const bool cw = is_word_byte(q[0]);
+        const bool pw = pos > 0 ? is_word_byte(prev) : false;
+        if (cw == pw) return;
+      }
+      if ((fl & kWordPrefix) && pos > 0 && is_word_byte(prev)) return;     // :195, :806
+      if ((fl & kLineStart) && pos > 0 && !is_line_end_byte(prev)) return; // :196, :807
+    }
+    pr.gram = __byte_perm(lds_le32(q), 0, 0x0123);
+    pr.flags = 1u | (cand_p ? 4u : 0u);
+    if (HAS_G4 && cand_g && T.len - pos >= 4) {
+      pr.flags |= 2u;
+      pr.bucket = (pr.gram * kHashMul) >> P.st.slot_shift;
+      pr.a = ldg_slot(P.st.slots + 2 * (size_t)pr.bucket);
+      pr.b = ldg_slot(P.st.slots + 2 * (size_t)pr.bucket + 1);
+    }
+  }
+
   template <typename Emit>
-  __device__ __forceinline__ void eval_position(const TileCtx &T, uint32_t tpos, bool cand_g, bool cand_p,
-                                                Emit &&emit) const {
+  __device__ __forceinline__ void probe_finish(const TileCtx &T, const Probe &pr, Emit &&emit) const {
+    if (!(pr.flags & 1u)) return;
+    const uint32_t tpos = pr.tpos, gram = pr.gram;
     const unsigned long long pos = T.p0 + tpos;
     const unsigned long long rem = T.len - pos;
     const uint8_t *q = T.sb + kTilePre + tpos;
-    const uint32_t prev = q[-1];
-    if (fl & kWordBoundary) { // matcher.c:770-776
-      const bool cw = is_word_byte(q[0]);
-      const bool pw = pos > 0 ? is_word_byte(prev) : false;
-      if (cw == pw) return;
-    }
-    if ((fl & kWordPrefix) && pos > 0 && is_word_byte(prev)) return;  // :195, :806
-    if ((fl & kLineStart) && pos > 0 && !is_line_end_byte(prev)) return; // :196, :807
-    const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
     bool emitted = false;
     const bool longest = fl & kLongestOnly;
 
-    if (HAS_G4 && cand_g && rem >= 4) {
-      uint32_t i = (gram * kHashMul) >> P.st.slot_shift;
-      uint4 s = ldg_slot(P.st.slots + i);
-      while (s.z != 0 && s.x != gram) {
-        i = (i + 1) & P.st.slot_mask;
-        s = ldg_slot(P.st.slots + i);
+    if (HAS_G4 && (pr.flags & 2u)) {
+      // bucketized linear probing: the key is in the first bucket (from its home) that has it;
+      // a bucket with a free slot ends the probe
+      uint4 a = pr.a, b = pr.b, s = make_uint4(0, 0, 0, 0);
+      uint32_t bucket = pr.bucket;
+      while (true) {
+        if (a.z != 0 && a.x == gram) {
+          s = a;
+          break;
+        }
+        if (b.z != 0 && b.x == gram) {
+          s = b;
+          break;
+        }
+        if (a.z == 0 || b.z == 0) break;
+        bucket = (bucket + 1) & P.st.slot_mask;
+        a = ldg_slot(P.st.slots + 2 * (size_t)bucket);
+        b = ldg_slot(P.st.slots + 2 * (size_t)bucket + 1);
       }
       if (s.z != 0) {
         const uint32_t meta = s.z;
         const uint32_t hay4 = lds_le32(q + 4);
         if (meta & kSlotValueMask) {
-          ++n_hits;
-          ++n_long_hits;
+          n_hits += stat_inc;
+          n_long_hits += stat_inc;
         }
         if (meta & kSlotMulti) {
           const uint32_t cnt = meta & kSlotValueMask;
@@ -208,7 +255,7 @@ struct Scanner {
             const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
             const uint32_t len = r.y;
             if (len > rem) continue; // matcher.c:203
-            ++n_cmp;
+            n_cmp += stat_inc;
             const uint32_t m = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
             if ((hay4 ^ r.x) & m) continue;
             if (len > 8 && !tail_equal(T, pos, len, r.z)) continue;
@@ -220,7 +267,7 @@ struct Scanner {
         } else {
           const uint32_t len = meta & kSlotValueMask;
           if (len != 0 && len <= rem) {
-            ++n_cmp;
+            n_cmp += stat_inc;
             const uint32_t m = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
             if (((hay4 ^ s.y) & m) == 0 && (len <= 8 || tail_equal(T, pos, len, s.w)) &&
                 end_ok_long(T, pos + len)) {
@@ -233,14 +280,14 @@ struct Scanner {
           if (end_ok_short(T, pos + 4, 4)) {
             emit(4u);
             emitted = true;
-            ++n_hits;
+            n_hits += stat_inc;
           } else {
-            ++n_miss;
+            n_miss += stat_inc;
           }
         }
       }
     }
-    if (HAS_P23 && cand_p && !(longest && emitted)) {
+    if (HAS_P23 && (pr.flags & 4u) && !(longest && emitted)) {
       if (P.st.n3 && rem >= 3) {
         const uint32_t k3 = gram >> 8;
         bool hit = false;
@@ -256,9 +303,9 @@ struct Scanner {
           if (end_ok_short(T, pos + 3, 3)) {
             emit(3u);
             emitted = true;
-            ++n_hits;
+            n_hits += stat_inc;
           } else {
-            ++n_miss;
+            n_miss += stat_inc;
           }
         }
       }
@@ -268,9 +315,9 @@ struct Scanner {
           if (end_ok_short(T, pos + 2, 2)) {
             emit(2u);
             emitted = true;
-            ++n_hits;
+            n_hits += stat_inc;
           } else {
-            ++n_miss;
+            n_miss += stat_inc;
           }
         }
       }
@@ -279,30 +326,24 @@ struct Scanner {
         if ((P.st.bitmap1[k1 >> 5] >> (k1 & 31)) & 1u) {
           if (end_ok_short(T, pos + 1, 1)) {
             emit(1u);
-            ++n_hits;
+            n_hits += stat_inc;
           } else {
-            ++n_miss;
+            n_miss += stat_inc;
           }
         }
       }
     }
   }
 
-  // One 512-byte chunk of a warp.  Returns the number of matches of the whole warp.
-  // direct == false: matches go to `stage` (packed, shared memory), at most kStageCap;
-  // direct == true : matches go to P.out[out_base ...] as final records.
-  __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t *stage,
-                                                 uint32_t stage_used, bool direct, unsigned long long out_base,
-                                                 unsigned long long emit_base, const uint32_t *map,
-                                                 uint32_t *overflow) const {
-    const uint32_t lpos = cbase + lane * 16;
+  // stage 1 for one lane: 16 positions -> candidate masks (bit k = position lpos + k)
+  __device__ __forceinline__ void stage1(const TileCtx &T, uint32_t lpos, uint32_t &cg, uint32_t &cp,
+                                         uint32_t &valid) const {
     const uint8_t *src = T.sb + kTilePre + lpos;
     const uint4 v = *reinterpret_cast<const uint4 *>(src);
     const uint32_t w4 = *reinterpret_cast<const uint32_t *>(src + 16);
     const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
-
-    // ---- stage 1: candidate masks
-    uint32_t cg = 0, cp = 0;
+    cg = 0;
+    cp = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
@@ -316,65 +357,116 @@ struct Scanner {
       }
     }
     const unsigned long long lp = T.p0 + lpos;
-    uint32_t valid = 0;
+    valid = 0;
     if (lp < T.end) valid = (T.end - lp >= 16) ? 0xFFFFu : ((1u << (uint32_t)(T.end - lp)) - 1u);
-    uint32_t cand = (cg | cp) & valid;
-    if (!__any_sync(kFull, cand)) return 0;
+  }
 
-    // ---- stage 2 + ordered emission (pass 0: count and cache, pass 1: the rest)
-    const uint32_t keep = direct ? 0u : 4u;
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    uint32_t n = 0, lane_base = 0, total = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      uint32_t idx = 0;
-      uint32_t m = cand;
-      while (m) {
-        const uint32_t k = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t tpos = lpos + k;
-        eval_position(T, tpos, (cg >> k) & 1u, (cp >> k) & 1u, [&](uint32_t len) {
-          if (pass == 0) {
-            const uint32_t e = (tpos << kPackLenBits) | len;
-            if (len >> kPackLenBits) *overflow = 1; // does not fit a staged entry -> direct pass
-            if (idx == 0) c0 = e;
-            else if (idx == 1) c1 = e;
-            else if (idx == 2) c2 = e;
-            else if (idx == 3) c3 = e;
-          } else if (idx >= keep) {
-            if (direct) {
-              const unsigned long long r = out_base + lane_base + idx;
-              if (r < P.out_cap) write_record(r, emit_base, tpos + T.p0, len, map);
-            } else if (lane_base + idx < kStageCap) {
-              stage[lane_base + idx] = (tpos << kPackLenBits) | len;
-            }
-          }
-          ++idx;
-        });
-      }
-      if (pass == 0) {
-        n = idx;
-        // warp exclusive prefix of n
-        uint32_t incl = n;
+  // One 512-byte chunk of a warp.  The warp's candidates are compacted into a queue in
+  // position order; then every lane takes one candidate per sub-step, kProbeUnroll sub-steps
+  // are issued together (their slot loads overlap), and accepted matches are appended in
+  // candidate order (ballot + popc; a shuffle scan only when a position has several matches;
+  // a position with more than four matches is evaluated a second time for the rest).
+  //   direct == false: matches go to `stage` (packed, shared memory, `cap` entries); when they
+  //                    do not fit, *overflow is set and the tile is redone with
+  //   direct == true : matches go to P.out[out_base ...] as final records.
+  // Returns the exact number of matches of the chunk in both modes.
+  static constexpr int kProbeUnroll = 4;
+  __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t *stage,
+                                                 uint32_t used, uint32_t cap, uint16_t *queue, bool direct,
+                                                 unsigned long long out_base, unsigned long long emit_base,
+                                                 const uint32_t *map, uint32_t *overflow) const {
+    uint32_t cg, cp, valid;
+    stage1(T, cbase + lane * 16, cg, cp, valid);
+    uint32_t cand = (cg | cp) & valid;
+    const uint32_t cnt = __popc(cand);
+    uint32_t incl = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t t = __shfl_up_sync(kFull, incl, d);
-          if (lane >= (uint32_t)d) incl += t;
-        }
-        total = __shfl_sync(kFull, incl, 31);
-        if (total == 0) break;
-        lane_base = stage_used + (incl - n);
-        if (!direct) {
-          if (stage_used + total > kStageCap) *overflow = 1;
-          if (n > 0 && lane_base + 0 < kStageCap) stage[lane_base + 0] = c0;
-          if (n > 1 && lane_base + 1 < kStageCap) stage[lane_base + 1] = c1;
-          if (n > 2 && lane_base + 2 < kStageCap) stage[lane_base + 2] = c2;
-          if (n > 3 && lane_base + 3 < kStageCap) stage[lane_base + 3] = c3;
-        }
-        if (!__any_sync(kFull, n > keep)) break;
-        if (n <= keep) cand = 0;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    if (total == 0) return 0;
+    {
+      uint32_t o = incl - cnt;
+      while (cand) {
+        const uint32_t k = __ffs(cand) - 1;
+        cand &= cand - 1;
+        queue[o++] = (uint16_t)((lane * 16 + k) | (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10));
       }
     }
-    return total;
+    __syncwarp();
+    uint32_t found = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < total; base += 32 * kProbeUnroll) {
+      Probe pr[kProbeUnroll];
+#pragma unroll
+      for (int u = 0; u < kProbeUnroll; ++u) {
+        const uint32_t idx = base + u * 32 + lane;
+        const bool ok = idx < total;
+        const uint32_t e = ok ? queue[idx] : 0u;
+        probe_issue(T, ok, cbase + (e & 511u), (e >> 9) & 1u, (e >> 10) & 1u, pr[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kProbeUnroll; ++u) {
+        if (base + u * 32 >= total) break;
+        uint32_t n = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        const uint32_t tpos = pr[u].tpos;
+        probe_finish(T, pr[u], [&](uint32_t len) {
+          if (n == 0) m0 = len;
+          else if (n == 1) m1 = len;
+          else if (n == 2) m2 = len;
+          else if (n == 3) m3 = len;
+          ++n;
+        });
+        const uint32_t bal = __ballot_sync(kFull, n > 0);
+        if (!bal) continue;
+        uint32_t pre, tot;
+        const bool many = __any_sync(kFull, n > 1);
+        if (!many) {
+          pre = __popc(bal & lt);
+          tot = __popc(bal);
+        } else {
+          uint32_t in2 = n;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, in2, d);
+            if (lane >= (uint32_t)d) in2 += t;
+          }
+          pre = in2 - n;
+          tot = __shfl_sync(kFull, in2, 31);
+        }
+        const uint32_t at = used + found + pre;
+        auto put = [&](uint32_t i, uint32_t len) {
+          if (direct) {
+            const unsigned long long r = out_base + at + i;
+            if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
+          } else if (at + i < cap && !(len >> kPackLenBits)) {
+            stage[at + i] = (tpos << kPackLenBits) | len;
+          } else {
+            *overflow = 1;
+          }
+        };
+        if (n > 0) put(0, m0);
+        if (n > 1) put(1, m1);
+        if (n > 2) put(2, m2);
+        if (n > 3) put(3, m3);
+        if (many && __any_sync(kFull, n > 4)) {
+          if (n > 4) { // evaluate the position again for matches 5, 6, ...
+            uint32_t i = 0;
+            stat_inc = 0;
+            probe_finish(T, pr[u], [&](uint32_t len) {
+              if (i >= 4) put(i, len);
+              ++i;
+            });
+            stat_inc = 1;
+          }
+        }
+        found += tot;
+      }
+    }
+    __syncwarp();
+    return found;
   }
 
   __device__ __forceinline__ void write_record(unsigned long long r, unsigned long long emit_base,
@@ -406,6 +498,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   uint32_t *g4s = reinterpret_cast<uint32_t *>(ring + S * kStageBytes);
   uint32_t *p23s = g4s + (HAS_G4 ? P.st.g4_words : 0);
   uint32_t *staging = p23s + (HAS_P23 ? P.st.p23_words : 0);
+  uint16_t *queues = reinterpret_cast<uint16_t *>(staging + kScanWarps * P.stage_cap);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t fl = P.flags;
@@ -473,7 +566,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   __syncthreads();
 
   Scanner<HAS_G4, HAS_P23> sc{P, g4s, p23s, fl};
-  uint32_t *my_stage = staging + warp * kStageCap;
+  const uint32_t cap = P.stage_cap;
+  uint32_t *my_stage = staging + warp * cap;
+  uint16_t *my_queue = queues + warp * kChunkBytes;
 
   for (uint32_t k = 0;; ++k) {
     const uint32_t s = k % S;
@@ -500,7 +595,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
       const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
       if (T.p0 + cbase >= T.end) break;
-      wc += sc.scan_chunk(T, cbase, lane, my_stage, wc, false, 0, emit_base, map, ovf);
+      wc += sc.scan_chunk(T, cbase, lane, my_stage, wc, cap, my_queue, false, 0, emit_base, map, ovf);
     }
     if (lane == 0) s_wcnt[warp] = wc;
     __syncthreads(); // (A) tile evaluated, counts visible
@@ -565,7 +660,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
         const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
         if (T.p0 + cbase >= T.end) break;
-        done += sc.scan_chunk(T, cbase, lane, my_stage, done, true, base, emit_base, map, &dummy);
+        done += sc.scan_chunk(T, cbase, lane, my_stage, done, cap, my_queue, true, base, emit_base, map, &dummy);
       }
       __syncthreads();
       if (tid == 32) produce(s);
@@ -598,13 +693,22 @@ cudaError_t launch_variant(const ScanParams &p, int grid, size_t smem, cudaStrea
 
 } // namespace
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages) {
-  return 512 + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kStagingBytes;
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t stage_cap) {
+  return 512 + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 +
+         size_t(kScanWarps) * stage_cap * 4 + kQueueBytes;
 }
 
-uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit) {
-  for (uint32_t s = 3; s >= 2; --s)
-    if (scan_smem_bytes(st, s) <= smem_limit) return s;
+uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *stage_cap) {
+  for (uint32_t s = 3; s >= 2; --s) {
+    if (scan_smem_bytes(st, s, kStageCapMin) > smem_limit) continue;
+    // whatever shared memory is left goes to the staging areas (denser matches before a tile
+    // has to be redone)
+    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
+    uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~31u;
+    if (cap > kStageCapMax) cap = kStageCapMax;
+    *stage_cap = cap;
+    return s;
+  }
   return 0;
 }
 
@@ -618,7 +722,7 @@ cudaError_t scan_configure(size_t smem_limit) {
 }
 
 cudaError_t scan_launch(const ScanParams &p, int grid, cudaStream_t stream) {
-  const size_t smem = scan_smem_bytes(p.st, p.stages);
+  const size_t smem = scan_smem_bytes(p.st, p.stages, p.stage_cap);
   const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0;
   if (g && q) return launch_variant<true, true>(p, grid, smem, stream);
   if (g) return launch_variant<true, false>(p, grid, smem, stream);

@@ -46,8 +46,9 @@ constexpr int kTileHalo = 112;                    // bytes staged behind a tile
 constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 32896 = 257*128
 constexpr int kWarpSpan = kTileBytes / kScanWarps; // 2048 positions per warp and tile
 constexpr int kChunkBytes = 512;                  // 32 lanes x 16 bytes
-constexpr int kStageCap = 512;                    // staged matches per warp and tile
-constexpr int kStagingBytes = kScanWarps * kStageCap * 4;
+constexpr uint32_t kStageCapMin = 256;            // staged matches per warp and tile: at least ...
+constexpr uint32_t kStageCapMax = 2048;           // ... at most (= one per position of the warp's span)
+constexpr int kQueueBytes = kScanWarps * kChunkBytes * 2; // per-warp candidate queue (u16 entries)
 constexpr int kSmemFixed = 256;
 constexpr uint32_t kPackLenBits = 17;             // staged entry = pos_in_tile << 17 | len
 
@@ -81,11 +82,12 @@ struct ScanParams {
   unsigned long long *counters; // [0] long-path attempts that found a bucket, ... (see engine)
   uint32_t flags;
   uint32_t stages;         // ring depth (2 or 3)
+  uint32_t stage_cap;      // staged matches per warp and tile
 };
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages);
-// chooses the deepest ring that fits; returns 0 if the filters do not fit at all
-uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit);
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t stage_cap);
+// chooses the deepest ring that fits (and the staging capacity); returns 0 if the filters do not fit at all
+uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *stage_cap);
 cudaError_t scan_launch(const ScanParams &p, int grid, cudaStream_t stream);
 cudaError_t scan_configure(size_t smem_limit);
 

@@ -126,12 +126,14 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
 
   // ---- slots: bucket grams first, then the 4-byte patterns are merged in
   const uint64_t n_keys_upper = buckets.size() + uint64_t(v.n4);
-  const uint32_t lg_slots = std::max<uint32_t>(4, ceil_log2(std::max<uint64_t>(1, n_keys_upper * 2)));
-  if (lg_slots > 30) return "too many distinct grams";
-  const uint32_t n_slots = 1u << lg_slots;
+  // buckets of two slots; capacity >= 2x the keys (4x while the table stays small)
+  uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, n_keys_upper)));
+  if (n_keys_upper <= (1u << 18)) ++lg_buckets;
+  if (lg_buckets > 29) return "too many distinct grams";
+  const uint32_t n_slots = 2u << lg_buckets;
   DeviceStore &d = s->params;
-  d.slot_shift = 32 - lg_slots;
-  d.slot_mask = n_slots - 1;
+  d.slot_shift = 32 - lg_buckets;
+  d.slot_mask = (1u << lg_buckets) - 1;
   s->slots.assign(n_slots, Slot{0, 0, 0, 0});
   s->recs.reserve(n_recs_multi);
 
@@ -142,10 +144,15 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     return w;
   };
   auto find_or_claim = [&](uint32_t gram) -> Slot & {
-    uint32_t i = slot_home(d, gram);
-    while (s->slots[i].meta != 0 && s->slots[i].key != gram) i = (i + 1) & d.slot_mask;
-    s->slots[i].key = gram;
-    return s->slots[i];
+    for (uint32_t b = slot_home(d, gram);; b = (b + 1) & d.slot_mask) {
+      for (uint32_t k = 0; k < 2; ++k) {
+        Slot &sl = s->slots[2 * size_t(b) + k];
+        if (sl.meta == 0 || sl.key == gram) {
+          sl.key = gram;
+          return sl;
+        }
+      }
+    }
   };
   uint32_t n_keys = 0;
   for (const BucketRef &b : buckets) {
@@ -264,9 +271,11 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
       const uint32_t b = g4_bit(d, gram);
       if (!(s.g4[b >> 5] >> (b & 31) & 1)) return nullptr;
     }
-    for (uint32_t i = slot_home(d, gram);; i = (i + 1) & d.slot_mask) {
-      if (s.slots[i].meta == 0) return nullptr;
-      if (s.slots[i].key == gram) return &s.slots[i];
+    for (uint32_t b = slot_home(d, gram);; b = (b + 1) & d.slot_mask) {
+      const Slot &x = s.slots[2 * size_t(b)], &y = s.slots[2 * size_t(b) + 1];
+      if (x.meta != 0 && x.key == gram) return &x;
+      if (y.meta != 0 && y.key == gram) return &y;
+      if (x.meta == 0 || y.meta == 0) return nullptr;
     }
   };
   for (uint64_t p = 0; p < v.hdr.blob_bytes;) {
