@@ -24,26 +24,20 @@ for r in rows[2:]:
     st = [(k, float(d[k])) for k in hdr if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio") and d[k] not in ("", "-nan", "nan")]
     for k, v in sorted(st, key=lambda x: -x[1])[:8]:
         print(f"  stall {k.split('stalled_')[1].split('_per_issue')[0]:28s} {v:8.2f}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-if len(rows) > 2:
-    h = rows[0]
-    try:
-        i_src = h.index("Source"); 
-    except ValueError:
-        i_src = 1
+hi = next((i for i, r in enumerate(rows) if r and r[0] == "Address"), None)
+if hi is not None:
+    h = rows[hi]
     cols = {n: i for i, n in enumerate(h)}
-    samp = cols.get("# Samples") or cols.get("Warp Stall Sampling (All Samples)") or cols.get("Sampling Data (All)")
-    inst = cols.get("Instructions Executed")
-    print("columns:", [c for c in h][:40])
-    if samp is not None:
-        agg = []
-        for r in rows[1:]:
-            try:
-                agg.append((float(r[samp] or 0), r))
-            except Exception:
-                pass
-        tot = sum(a for a, _ in agg) or 1
-        print(f"-- hottest lines by samples (total {tot:.0f})")
-        for a, r in sorted(agg, key=lambda x: -x[0])[:nlines]:
-            print(f"  {100*a/tot:5.1f}%  inst={r[inst] if inst is not None else '?':>12s}  {r[i_src][:150]}")
+    i_src, samp, inst, thr = cols["Source"], cols["# Samples"], cols["Instructions Executed"], cols["Avg. Threads Executed"]
+    body = [r for r in rows[hi + 1:] if len(r) > samp and r[0].startswith("0x")]
+    tot = sum(float(r[samp] or 0) for r in body) or 1
+    tin = sum(float(r[inst] or 0) for r in body) or 1
+    print(f"-- SASS: {len(body)} instructions, {tin:.3g} warp-instructions executed, {tot:.0f} samples")
+    print("-- hottest SASS by stall samples")
+    for r in sorted(body, key=lambda r: -float(r[samp] or 0))[:nlines]:
+        print(f"  {100*float(r[samp] or 0)/tot:5.1f}%  exec={float(r[inst] or 0)/tin*100:5.2f}%  thr={r[thr]:>5s}  {r[0][-5:]}  {r[i_src].strip()[:110]}")
+    print("-- most executed SASS")
+    for r in sorted(body, key=lambda r: -float(r[inst] or 0))[:nlines]:
+        print(f"  exec={float(r[inst] or 0)/tin*100:5.2f}%  samples={100*float(r[samp] or 0)/tot:5.1f}%  thr={r[thr]:>5s}  {r[0][-5:]}  {r[i_src].strip()[:110]}")
