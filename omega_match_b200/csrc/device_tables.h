@@ -4,31 +4,42 @@
 // slots, so nothing of the file is used in place.  At create() the store is
 // re-staged into:
 //
-//   slots[]   one 16-byte record per distinct gram in BUCKETS of two (one 32-byte sector):
-//             a gram lives in the first bucket, counted from its home bucket, that had a free
-//             slot when it was inserted; a probe stops at the first bucket with a free slot.
-//             Load <= 0.5, so most probes -- hit or miss -- cost one sector.  A slot holds
-//             everything the scan needs to REJECT a candidate with one 16-byte load: the
-//             gram, pattern bytes 4..7 and the length of the (longest) pattern.  Grams of
-//             4-byte patterns live in the same table (flag bit) -> the length-4 short matcher
-//             (matcher.c:685-692, a binary search) becomes the same probe.
-//   recs[]    for buckets with more than one pattern: 16-byte records, longest first
-//             (the order compiler.c:271 gives the bucket).
+//   keys[]    the exact gram set: BUCKETS of four 32-bit grams (16 bytes, one vector load).  A
+//             gram lives in the first bucket, counted from its home bucket, that had a free
+//             place when it was inserted; places fill left to right, so a bucket whose last
+//             place holds `empty_key` ends a probe.  Load <= 0.25: a probe -- hit or miss --
+//             costs one 16-byte load in ~98% of the cases.  This is the table almost every
+//             candidate dies in, so it holds nothing but keys (role of probe_bucket,
+//             hash_table.c:91-109).  `empty_key` is a value that is not a gram of the store.
+//   slots[]   parallel to keys[] (slot = 4*bucket + place), read only after a key hit: pattern
+//             bytes 4..11 and the length of the (single) pattern, so that a pattern of up to
+//             12 bytes is verified without touching the pattern store, or a reference to
+//   recs[]    for grams shared by several patterns: 16-byte records, longest first (the order
+//             compiler.c:271 gives the bucket).  Grams of 4-byte patterns live in the same
+//             table (flag bit) -> the length-4 short matcher (matcher.c:685-692, a binary
+//             search) becomes the same probe.
 //   store[]   pattern bytes, padded so 4-byte reads never leave the allocation.
-//   g4[]      single-probe hashed bitmap over every gram in slots[] -- a superset filter with
+//   g4[]      single-probe hashed bitmap over every gram in keys[] -- a superset filter with
 //             no false negatives, copied into shared memory by every CTA.  It stands in for
 //             the reference's 3-probe Bloom (bloom.c:51-64): same role, one probe, sized to
 //             fit on chip; which positions reach the exact table changes, the match set not.
 //   p23[]     one hashed bitmap for the 1..3 byte patterns (exact membership is then checked
 //             against bitmap1/bitmap2 of the file and a hash set of the 3-byte keys).
+//   cls       optional byte-class prefilter for stores without 1..3 byte patterns: every
+//             pattern starts with `cls_run` bytes that all fall into at most two byte ranges
+//             (after an optional fold of bit 5) -- e.g. letters only.  A position whose next
+//             cls_run bytes are not all in the class cannot start a match and never reaches
+//             the filters.  Evaluated with SWAR arithmetic on the registers that hold the
+//             haystack words, no table.
 #pragma once
 #include <cstdint>
+#include <vector_types.h>
 
 namespace olm {
 
 struct alignas(16) Slot {
-  uint32_t key;   // big-endian gram (util.h:23-26)
   uint32_t next4; // pattern bytes 4..7 as a little-endian word, zero padded (single-pattern slots)
+  uint32_t next8; // pattern bytes 8..11, same
   uint32_t meta;  // 0 = empty; see kSlot* below
   uint32_t ref;   // single: offset of the pattern in store[]; multi: first index in recs[]
 };
@@ -40,13 +51,23 @@ struct alignas(16) Rec {
   uint32_t next4;
   uint32_t len;
   uint32_t store_off;
-  uint32_t _pad;
+  uint32_t next8;
 };
 
-constexpr uint32_t kHashMul = 0x9E3779B1u; // one multiply feeds both the g4 filter and the slot index
+constexpr uint32_t kHashMul = 0x9E3779B1u; // one multiply feeds both the g4 filter and the bucket index
+
+// Byte-class prefilter: byte b is in the class iff, with t = b & and_mask (and_mask clears bit 7
+// and optionally bit 5), lo[i] <= t <= hi[i] for one of the n_ranges ranges, and b < 0x80.
+struct ByteClass {
+  uint32_t run = 0;      // 0 = disabled; else 4, 5, 6 or 8: that many leading pattern bytes are in the class
+  uint32_t and_mask = 0; // 0x7f or 0x5f
+  uint32_t n_ranges = 0; // 1 or 2
+  uint32_t lo[2] = {0, 0}, hi[2] = {0, 0};
+};
 
 // Everything the scan kernel needs to know about the store; passed by value.
 struct DeviceStore {
+  const uint4 *keys = nullptr;
   const Slot *slots = nullptr;
   const Rec *recs = nullptr;
   const uint8_t *store = nullptr;
@@ -55,14 +76,16 @@ struct DeviceStore {
   const uint32_t *set3 = nullptr;    // open addressing, value = key3 + 1, 0 = empty
   const uint32_t *bitmap2 = nullptr; // 2048 words, bit (b0<<8|b1) as in short_matcher_t
   uint32_t bitmap1[8] = {0};         // bit b as in short_matcher_t
-  uint32_t slot_shift = 32;          // home BUCKET = (gram*kHashMul) >> slot_shift; slots 2b, 2b+1
-  uint32_t slot_mask = 0;            // number of buckets - 1
+  uint32_t key_shift = 32;           // home bucket = (gram*kHashMul) >> key_shift
+  uint32_t key_mask = 0;             // number of buckets - 1
+  uint32_t empty_key = 0;
   uint32_t g4_shift = 32, g4_words = 0;
   uint32_t p23_and = 0, p23_mul = 1, p23_shift = 32, p23_words = 0;
   uint32_t set3_mask = 0;
   uint32_t n_long = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0;
   uint32_t smallest = 0, largest = 0;
   uint32_t flags = 0;
+  ByteClass cls;
 };
 
 } // namespace olm

@@ -84,8 +84,8 @@ struct EngineImpl {
   DeviceStore ds;
   uint32_t stages = 0, stage_cap = 0;
   bool has_short_234 = false;
-  DevBuf d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, tile_state, misc, norm, map, windows, ghost, fscratch;
+  DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
+  DevBuf hay, out, out2, tile_state, redo, misc, norm, map, windows, ghost, fscratch;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -133,6 +133,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   impl->has_short_234 = view.n2 || view.n3 || view.n4;
   impl->ds = staged.params;
   bool ok = true;
+  ok = ok && upload(impl->d_keys, staged.keys, &impl->ds.keys) == 0;
   ok = ok && upload(impl->d_slots, staged.slots, &impl->ds.slots) == 0;
   ok = ok && upload(impl->d_recs, staged.recs, &impl->ds.recs) == 0;
   ok = ok && upload(impl->d_store, staged.store, &impl->ds.store) == 0;
@@ -161,8 +162,8 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
 Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
-  for (DevBuf *b : {&impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
-                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->tile_state, &impl_->misc,
+  for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->tile_state, &impl_->redo, &impl_->misc,
                     &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch})
     b->release();
   for (auto &ev : impl_->ev)
@@ -208,10 +209,14 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     return -1;
   }
   if (E.tile_state.ensure((tiles + 1) * 8)) return -1;
-  // misc: [0..n_batches) u32 tickets | @ 256 KiB: total (u64), filter total (u64), counters[8]
-  const size_t misc_total_off = size_t(kMaxBatches) * 4;
+  // misc: [0..kMaxBatches) u32 tickets | [..2*kMaxBatches) u32 redo counts | total (u64),
+  // filter total (u64), counters[8]
+  const size_t misc_total_off = size_t(kMaxBatches) * 8;
   if (E.misc.ensure(misc_total_off + 256)) return -1;
   unsigned int *d_tickets = static_cast<unsigned int *>(E.misc.p);
+  unsigned int *d_redo_counts = d_tickets + kMaxBatches;
+  const uint64_t tiles_per_launch = windowed ? uint64_t(kBatchWindows) * kTilesPerWindow : tiles;
+  if (E.redo.ensure((tiles_per_launch + 1) * 4)) return -1;
   unsigned long long *d_total = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + misc_total_off);
   unsigned long long *d_ftotal = d_total + 1;
   unsigned long long *d_counters = d_total + 2;
@@ -242,7 +247,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     if (E.out.ensure(cap * sizeof(Record))) return -1;
     cap = E.out.cap / sizeof(Record);
     OLM_CUDA(cudaMemsetAsync(E.tile_state.p, 0, (tiles + 1) * 8, E.stream));
-    OLM_CUDA(cudaMemsetAsync(E.misc.p, 0, n_batches * 4, E.stream));
+    OLM_CUDA(cudaMemsetAsync(d_tickets, 0, n_batches * 4, E.stream));
+    OLM_CUDA(cudaMemsetAsync(d_redo_counts, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_total, 0, 128, E.stream));
     uint32_t launches = 0, scan_launches = 0;
     OLM_CUDA(cudaEventRecord(E.ev[0], E.stream));
@@ -259,6 +265,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.stages = E.stages;
     P.stage_cap = E.stage_cap;
     P.tail_byte = 0;
+    P.redo_list = static_cast<uint32_t *>(E.redo.p);
 
     if (!windowed) {
       P.buf = static_cast<const uint8_t *>(r.dev);
@@ -270,9 +277,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
       P.num_tiles = (uint32_t)tiles;
       P.tile_base = 0;
       P.ticket = d_tickets;
-      const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)E.sms);
-      OLM_CUDA(scan_launch(P, grid, E.stream));
-      ++launches;
+      P.redo_count = d_redo_counts;
+      OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
       ++scan_launches;
     } else {
       float tf_ms = 0.f;
@@ -304,9 +310,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.num_tiles = nw * kTilesPerWindow;
         P.tile_base = (uint32_t)(w0 * kTilesPerWindow);
         P.ticket = d_tickets + b;
-        const int grid = (int)std::min<uint64_t>(P.num_tiles, (uint64_t)E.sms);
-        OLM_CUDA(scan_launch(P, grid, E.stream));
-        ++launches;
+        P.redo_count = d_redo_counts + b;
+        OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
         ++scan_launches;
       }
     }
@@ -416,9 +421,9 @@ int64_t Engine::no_overlap_inplace(void *dev_records, uint64_t count) {
   if (count < 2) return (int64_t)count;
   if (E.out2.ensure(count * sizeof(Record))) return -1;
   if (E.fscratch.ensure(filter_scratch_bytes(count))) return -1;
-  if (E.misc.ensure(size_t(kMaxBatches) * 4 + 256)) return -1;
+  if (E.misc.ensure(size_t(kMaxBatches) * 8 + 256)) return -1;
   unsigned long long *d_ftotal =
-      reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + size_t(kMaxBatches) * 4) + 1;
+      reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + size_t(kMaxBatches) * 8) + 1;
   uint32_t launches = 0;
   unsigned long long total = 0;
   OLM_CUDA(no_overlap_launch(static_cast<const Record *>(dev_records), count, static_cast<Record *>(E.out2.p),

@@ -6,25 +6,33 @@
 // :804-880) and -- because matches leave the kernel already in final order -- the
 // concatenate + radix sort of finalize_match_results (matcher.c:587-623, :258-325).
 //
-// Shape of the kernel
-//   * persistent CTAs (grid = #SMs), 512 threads; tiles of 32 KiB positions are handed out
-//     by an atomic ticket, so tile k is always started before tile k+1;
-//   * each tile (+16 bytes in front, +112 behind) is brought into shared memory by ONE
-//     cp.async.bulk (TMA, 1-D) that completes on an mbarrier; a ring of 2-3 stages keeps
-//     60-100 KiB per SM in flight;
-//   * stage 1, every position: big-endian gram by PRMT from two registers, one multiply,
-//     one probe of the hashed gram bitmap in shared memory (and one of the short-pattern
-//     bitmap when the store has 1..3 byte patterns) -> 16-bit candidate masks per lane;
-//   * stage 2, candidates only: position predicates, ONE 16-byte slot load that carries
-//     gram + bytes 4..7 + length (rejects almost every false candidate), remaining bytes
-//     against the pattern store, end predicates, then the 4/3/2/1-byte sets;
-//   * emission: a lane keeps up to four matches in registers, the warp prefix-sums the
-//     counts, matches go to the warp's private staging area in position order; at the end
-//     of the tile a decoupled look-back over the tile descriptors yields the tile's global
-//     base and every warp copies its staged matches to their FINAL place in the result
-//     array: offset ascending, length descending, no sort pass.
-//   * a tile whose matches do not fit the staging area is re-evaluated once, writing to
-//     HBM directly (counts are always exact, so the result is the same).
+// Shape of scan_kernel
+//   * persistent CTAs (grid = #SMs): 16 scanning warps + 1 control warp.  Tiles of 16 KiB
+//     positions are handed out by an atomic ticket, so tile k is always started before k+1;
+//   * control warp, producer half: each tile (+16 bytes in front, +112 behind) is brought into
+//     shared memory by ONE cp.async.bulk (TMA, 1-D) that completes on a `full` mbarrier; a ring
+//     of up to 4 stages keeps ~64 KiB per SM in flight; a stage is refilled as soon as all 16
+//     scanning warps have arrived on its `scanned` mbarrier -- no CTA-wide barrier anywhere;
+//   * stage 1, every position, in registers:
+//       - stores whose patterns all start with a run of bytes from a small class (letters ...):
+//         SWAR range tests on the haystack words -> 1 bit per position (no memory access);
+//       - else: big-endian gram by PRMT from two registers, one multiply, one probe of the
+//         hashed gram bitmap in shared memory (and one of the short-pattern bitmap when the
+//         store has 1..3 byte patterns);
+//     survivors are compacted, in position order, into the warp's queue;
+//   * stage 2, queue entries, 32 x kProbeUnroll at a time: position predicates, (class mode:
+//     the gram bitmap probe,) ONE 16-byte load of the gram's key bucket -- almost every false
+//     candidate ends here --, on a key hit the slot (pattern bytes 4..11 + length), remaining
+//     bytes against the pattern store, end predicates, then the 4/3/2/1-byte sets;
+//   * emission: accepted matches are appended in candidate order (ballot + popc) to the warp's
+//     staging area of the tile (two areas per warp, tiles alternate);
+//   * control warp, look-back half: warp totals of tile k -> exclusive prefixes, a decoupled
+//     look-back over the tile descriptors yields the tile's global base; the scanning warps
+//     copy tile k's staged matches to their FINAL place in the result array (offset
+//     ascending, length descending: no sort pass) after they have scanned tile k+1;
+//   * a tile whose matches do not fit the staging area goes on the redo list; redo_kernel
+//     (launched right after, exits at once when the list is empty) re-evaluates such tiles
+//     and writes to HBM directly (counts are always exact, so bases do not change).
 #include "scan.cuh"
 
 #include <cstdio>
@@ -40,18 +48,41 @@ constexpr unsigned long long kStateAggregate = 1ull << 62;
 constexpr unsigned long long kStatePrefix = 2ull << 62;
 constexpr unsigned long long kStateValueMask = (1ull << 62) - 1;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 
-struct StageInfo { // written by the producer thread, read by everyone after the mbarrier wait
+struct StageInfo { // written by the producer lane, read by everyone after the mbarrier wait
   unsigned long long p0;   // segment-relative position of the tile's first byte
   unsigned long long len;  // segment length (N, or M_w)
   unsigned long long end;  // one past the last start position to evaluate
   long long boff;          // buffer offset of position p0
   unsigned long long emit_base;
-  uint32_t tile;           // launch-local tile index
+  uint32_t tile;           // launch-local tile index, kNoTile = no more work
   uint32_t tail;
   uint32_t win;
   uint32_t staged;         // bytes valid behind p0 in the stage buffer
+  uint32_t _pad[2];
 };
+static_assert(sizeof(StageInfo) == 64, "StageInfo is 64 bytes");
+
+struct TileOut { // what the copy-out of a tile needs after its stage has been refilled
+  unsigned long long p0, emit_base;
+  uint32_t win, _pad;
+};
+
+// shared memory header (kSmemHeader bytes)
+struct SmemHeader {
+  uint64_t full[kMaxStages];
+  uint64_t scanned[kMaxStages];
+  uint64_t ready[2];
+  uint32_t ovf[2];       // set by scanning warps while they stage a tile
+  uint32_t ovf_final[2]; // what the copy-out looks at
+  unsigned long long base[2];
+  uint32_t wcnt[2][kScanWarps];
+  uint32_t wpre[2][kScanWarps];
+  TileOut tout[2];
+  StageInfo info[kMaxStages];
+};
+static_assert(sizeof(SmemHeader) <= kSmemHeader, "header does not fit");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -62,6 +93,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
@@ -87,19 +121,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire(const unsigned long long *p) {
+// Tile descriptors carry their whole payload in one 64-bit word, so relaxed accesses are
+// enough (nothing else written by the other CTA is read) -- and, unlike acquire loads, they do
+// not make ptxas invalidate L1 (CCTL.IVALL) on every poll.
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
   unsigned long long v;
-  asm volatile("ld.global.acquire.gpu.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.global.release.gpu.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// 16-byte slot load through the read-only path.  (ld.global.nc.L1::no_allocate was tried: the
-// 32 MiB table of the 1M-pattern store then stopped being retained by L2 -- hit rate 95% -> 25%,
-// 61 GB of DRAM reads per GiB scanned, profiles/r1_notes.md -- so the default policy stays.)
-__device__ __forceinline__ uint4 ldg_slot(const Slot *p) {
-  return __ldg(reinterpret_cast<const uint4 *>(p));
+__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // little-endian 32-bit word at an arbitrary shared-memory byte address
@@ -113,53 +144,75 @@ __device__ __forceinline__ uint32_t lds_le32(const uint8_t *q) {
 
 struct TileCtx {
   const uint8_t *sb; // stage buffer; sb[kTilePre + i] is the byte at tile position i
-  unsigned long long p0, len, end;
+  unsigned long long p0;
   long long boff;
+  uint32_t rem0;   // min(len - p0, 2^31): bytes of the segment from the tile's first position on
+  uint32_t nscan;  // positions of this tile to evaluate (<= kTileBytes)
   uint32_t staged, tail;
+  bool first;      // p0 == 0
 };
 
-template <bool HAS_G4, bool HAS_P23>
+enum ChunkMode { kStageMode = 0, kCountMode = 1, kDirectMode = 2 };
+
+// SWAR constants of the byte-class prefilter (device_tables.h ByteClass), replicated per byte
+struct ClassRegs {
+  uint32_t and4, addlo0, addhi0, addlo1, addhi1, run;
+  bool two;
+};
+
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
 struct Scanner {
   const ScanParams &P;
   const uint32_t *g4s;
   const uint32_t *p23s;
   const uint32_t fl;
+  ClassRegs C;
   // statistics of omega_match_stats_t that cost nothing extra (list_matcher.h:43-49):
   // hits = buckets found + short matches accepted, misses = short candidates rejected by a
   // predicate, comparisons = bucket patterns that fit (matcher.c:783-799, :818-877, :210)
   mutable uint32_t n_hits = 0, n_miss = 0, n_cmp = 0, n_long_hits = 0;
   mutable uint32_t stat_inc = 1; // 0 while a position is evaluated a second time
 
-  __device__ __forceinline__ uint32_t hay_byte(const TileCtx &T, unsigned long long pos) const {
-    const unsigned long long rel = pos - T.p0;
+  __device__ __forceinline__ Scanner(const ScanParams &p, const uint32_t *g4, const uint32_t *p23)
+      : P(p), g4s(g4), p23s(p23), fl(p.flags) {
+    const ByteClass &c = p.st.cls;
+    C.and4 = c.and_mask * 0x01010101u;
+    C.addlo0 = (0x80u - c.lo[0]) * 0x01010101u;
+    C.addhi0 = (0x7Fu - c.hi[0]) * 0x01010101u;
+    C.addlo1 = (0x80u - c.lo[1]) * 0x01010101u;
+    C.addhi1 = (0x7Fu - c.hi[1]) * 0x01010101u;
+    C.two = c.n_ranges > 1;
+    C.run = c.run;
+  }
+
+  __device__ __forceinline__ uint32_t hay_byte(const TileCtx &T, uint32_t rel) const {
     if (rel < T.staged) return T.sb[kTilePre + rel];
     return P.buf[T.boff + (long long)rel];
   }
 
-  // bytes [8, len) of a candidate against the pattern store (bytes 0..7 are already equal)
-  __device__ __forceinline__ bool tail_equal(const TileCtx &T, unsigned long long pos, uint32_t len,
-                                             uint32_t store_off) const {
+  // bytes [12, len) of a candidate against the pattern store (bytes 0..11 are already equal)
+  __device__ __forceinline__ bool tail_equal(const TileCtx &T, uint32_t tpos, uint32_t len, uint32_t store_off) const {
     const uint8_t *pat = P.st.store + store_off;
-    for (uint32_t i = 8; i < len; ++i)
-      if (hay_byte(T, pos + i) != __ldg(pat + i)) return false;
+    for (uint32_t i = 12; i < len; ++i)
+      if (hay_byte(T, tpos + i) != __ldg(pat + i)) return false;
     return true;
   }
 
   // end-side predicates for a long match (matcher.c:233, :239, :247): all guarded by e < n
-  __device__ __forceinline__ bool end_ok_long(const TileCtx &T, unsigned long long e) const {
+  __device__ __forceinline__ bool end_ok_long(const TileCtx &T, uint32_t tpos, uint32_t len) const {
     if (!(fl & (kWordBoundary | kWordSuffix | kLineEnd))) return true;
-    if (e >= T.len) return true;
-    const uint32_t c = hay_byte(T, e);
+    if (tpos + len >= T.rem0) return true;
+    const uint32_t c = hay_byte(T, tpos + len);
     if ((fl & (kWordBoundary | kWordSuffix)) && is_word_byte(c)) return false;
     if ((fl & kLineEnd) && !is_line_end_byte(c)) return false;
     return true;
   }
   // short matcher, matcher.c:804-880: for lengths 2..4 the word-boundary test reads
   // haystack[pos+L] without a bound (:812,:830,:848) -> `tail` stands in at pos+L == n.
-  __device__ __forceinline__ bool end_ok_short(const TileCtx &T, unsigned long long e, uint32_t L) const {
+  __device__ __forceinline__ bool end_ok_short(const TileCtx &T, uint32_t tpos, uint32_t L) const {
     if (!(fl & (kWordBoundary | kWordSuffix | kLineEnd))) return true;
-    const bool inside = e < T.len;
-    const uint32_t c = inside ? hay_byte(T, e) : T.tail;
+    const bool inside = tpos + L < T.rem0;
+    const uint32_t c = inside ? hay_byte(T, tpos + L) : T.tail;
     if (fl & kWordBoundary) {
       if (L == 1) {
         if (inside && is_word_byte(c)) return false;
@@ -173,13 +226,13 @@ struct Scanner {
   }
 
   // ---- one candidate position, split in two so that several probes can be in flight ----
-  // probe_issue : position predicates (matcher.c:770-776, :195-196, :806-807), the gram, and
-  //               the loads of the candidate's home bucket (two 16-byte slots = one sector);
+  // probe_issue : position predicates (matcher.c:770-776, :195-196, :806-807), the gram,
+  //               (class mode: the gram bitmap,) and the load of the gram's key bucket;
   // probe_finish: everything else the reference does for the position (matcher.c:782-880);
   //               `emit(len)` is called once per accepted match, longest first.
   struct Probe {
     uint32_t tpos, gram, bucket, flags; // flags: 1 = alive, 2 = gram candidate (and >= 4 bytes left), 4 = short candidate
-    uint4 a, b;
+    uint4 kb;
   };
 
   __device__ __forceinline__ void probe_issue(const TileCtx &T, bool valid, uint32_t tpos, bool cand_g, bool cand_p,
@@ -188,28 +241,32 @@ struct Scanner {
     pr.flags = 0;
     pr.gram = 0;
     pr.bucket = 0;
-    pr.a = make_uint4(0, 0, 0, 0);
-    pr.b = make_uint4(0, 0, 0, 0);
+    pr.kb = make_uint4(0, 0, 0, 0);
     if (!valid) return;
-    const unsigned long long pos = T.p0 + tpos;
     const uint8_t *q = T.sb + kTilePre + tpos;
     if (fl & (kWordBoundary | kWordPrefix | kLineStart)) {
+      const bool at0 = T.first && tpos == 0;
       const uint32_t prev = q[-1];
       if (fl & kWordBoundary) { // matcher.c:770-776
         const bool cw = is_word_byte(q[0]);
-        const bool pw = pos > 0 ? is_word_byte(prev) : false;
+        const bool pw = at0 ? false : is_word_byte(prev);
         if (cw == pw) return;
       }
-      if ((fl & kWordPrefix) && pos > 0 && is_word_byte(prev)) return;     // :195, :806
-      if ((fl & kLineStart) && pos > 0 && !is_line_end_byte(prev)) return; // :196, :807
+      if ((fl & kWordPrefix) && !at0 && is_word_byte(prev)) return;     // :195, :806
+      if ((fl & kLineStart) && !at0 && !is_line_end_byte(prev)) return; // :196, :807
     }
-    pr.gram = __byte_perm(lds_le32(q), 0, 0x0123);
+    const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
+    pr.gram = gram;
     pr.flags = 1u | (cand_p ? 4u : 0u);
-    if (HAS_G4 && cand_g && T.len - pos >= 4) {
+    if (HAS_G4 && cand_g && T.rem0 - tpos >= 4) {
+      const uint32_t h = gram * kHashMul;
+      if (HAS_CLS) { // the queue holds class survivors: the gram bitmap is probed here
+        const uint32_t b = h >> P.st.g4_shift;
+        if (!((g4s[b >> 5] >> (b & 31)) & 1u)) return;
+      }
       pr.flags |= 2u;
-      pr.bucket = (pr.gram * kHashMul) >> P.st.slot_shift;
-      pr.a = ldg_slot(P.st.slots + 2 * (size_t)pr.bucket);
-      pr.b = ldg_slot(P.st.slots + 2 * (size_t)pr.bucket + 1);
+      pr.bucket = h >> P.st.key_shift;
+      pr.kb = __ldg(P.st.keys + pr.bucket);
     }
   }
 
@@ -217,72 +274,71 @@ struct Scanner {
   __device__ __forceinline__ void probe_finish(const TileCtx &T, const Probe &pr, Emit &&emit) const {
     if (!(pr.flags & 1u)) return;
     const uint32_t tpos = pr.tpos, gram = pr.gram;
-    const unsigned long long pos = T.p0 + tpos;
-    const unsigned long long rem = T.len - pos;
+    const uint32_t rem = T.rem0 - tpos;
     const uint8_t *q = T.sb + kTilePre + tpos;
     bool emitted = false;
     const bool longest = fl & kLongestOnly;
 
     if (HAS_G4 && (pr.flags & 2u)) {
-      // bucketized linear probing: the key is in the first bucket (from its home) that has it;
-      // a bucket with a free slot ends the probe
-      uint4 a = pr.a, b = pr.b, s = make_uint4(0, 0, 0, 0);
+      // the gram is in the first bucket (from its home) that has it; a bucket whose last
+      // place is unused ends the probe
+      uint4 kb = pr.kb;
       uint32_t bucket = pr.bucket;
+      int place = -1;
       while (true) {
-        if (a.z != 0 && a.x == gram) {
-          s = a;
-          break;
-        }
-        if (b.z != 0 && b.x == gram) {
-          s = b;
-          break;
-        }
-        if (a.z == 0 || b.z == 0) break;
-        bucket = (bucket + 1) & P.st.slot_mask;
-        a = ldg_slot(P.st.slots + 2 * (size_t)bucket);
-        b = ldg_slot(P.st.slots + 2 * (size_t)bucket + 1);
+        place = kb.x == gram ? 0 : kb.y == gram ? 1 : kb.z == gram ? 2 : kb.w == gram ? 3 : -1;
+        if (place >= 0 || kb.w == P.st.empty_key) break;
+        bucket = (bucket + 1) & P.st.key_mask;
+        kb = __ldg(P.st.keys + bucket);
       }
-      if (s.z != 0) {
-        const uint32_t meta = s.z;
-        const uint32_t hay4 = lds_le32(q + 4);
-        if (meta & kSlotValueMask) {
-          n_hits += stat_inc;
-          n_long_hits += stat_inc;
-        }
-        if (meta & kSlotMulti) {
-          const uint32_t cnt = meta & kSlotValueMask;
-          for (uint32_t j = 0; j < cnt; ++j) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
-            const uint32_t len = r.y;
-            if (len > rem) continue; // matcher.c:203
-            n_cmp += stat_inc;
-            const uint32_t m = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
-            if ((hay4 ^ r.x) & m) continue;
-            if (len > 8 && !tail_equal(T, pos, len, r.z)) continue;
-            if (!end_ok_long(T, pos + len)) continue;
-            emit(len);
-            emitted = true;
-            if (longest) break;
+      if (place >= 0) {
+        const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + (4 * (size_t)bucket + place)));
+        const uint32_t meta = s.z; // 0 when the gram equals empty_key and matched an unused place
+        if (meta != 0) {
+          const uint32_t hay4 = lds_le32(q + 4), hay8 = lds_le32(q + 8);
+          if (meta & kSlotValueMask) {
+            n_hits += stat_inc;
+            n_long_hits += stat_inc;
           }
-        } else {
-          const uint32_t len = meta & kSlotValueMask;
-          if (len != 0 && len <= rem) {
-            n_cmp += stat_inc;
-            const uint32_t m = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
-            if (((hay4 ^ s.y) & m) == 0 && (len <= 8 || tail_equal(T, pos, len, s.w)) &&
-                end_ok_long(T, pos + len)) {
+          // bytes 4..11 of a pattern of length len against the haystack
+          auto head_equal = [&](uint32_t len, uint32_t n4, uint32_t n8) {
+            const uint32_t m4 = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
+            const uint32_t m8 = len >= 12 ? kFull : (len > 8 ? ((1u << ((len - 8) * 8)) - 1u) : 0u);
+            return (((hay4 ^ n4) & m4) | ((hay8 ^ n8) & m8)) == 0;
+          };
+          if (meta & kSlotMulti) {
+            const uint32_t cnt = meta & kSlotValueMask;
+            for (uint32_t j = 0; j < cnt; ++j) {
+              const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
+              const uint32_t len = r.y;
+              if (len > rem) continue; // matcher.c:203
+              n_cmp += stat_inc;
+              if (!head_equal(len, r.x, r.w)) continue;
+              if (len > 12 && !tail_equal(T, tpos, len, r.z)) continue;
+              if (!end_ok_long(T, tpos, len)) continue;
               emit(len);
               emitted = true;
+              if (longest) break;
+            }
+          } else {
+            const uint32_t len = meta & kSlotValueMask;
+            if (len != 0 && len <= rem) {
+              n_cmp += stat_inc;
+              if (head_equal(len, s.x, s.y) && (len <= 12 || tail_equal(T, tpos, len, s.w)) &&
+                  end_ok_long(T, tpos, len)) {
+                emit(len);
+                emitted = true;
+              }
             }
           }
-        }
-        if ((meta & kSlotShort4) && !(longest && emitted)) {
-          if (end_ok_short(T, pos + 4, 4)) {
-            emit(4u);
-            emitted = true;
-            n_hits += stat_inc;
-          } else {
-            n_miss += stat_inc;
+          if ((meta & kSlotShort4) && !(longest && emitted)) {
+            if (end_ok_short(T, tpos, 4)) {
+              emit(4u);
+              emitted = true;
+              n_hits += stat_inc;
+            } else {
+              n_miss += stat_inc;
+            }
           }
         }
       }
@@ -300,7 +356,7 @@ struct Scanner {
           }
         }
         if (hit) {
-          if (end_ok_short(T, pos + 3, 3)) {
+          if (end_ok_short(T, tpos, 3)) {
             emit(3u);
             emitted = true;
             n_hits += stat_inc;
@@ -312,7 +368,7 @@ struct Scanner {
       if (P.st.n2 && rem >= 2 && !(longest && emitted)) {
         const uint32_t k2 = gram >> 16;
         if ((__ldg(P.st.bitmap2 + (k2 >> 5)) >> (k2 & 31)) & 1u) {
-          if (end_ok_short(T, pos + 2, 2)) {
+          if (end_ok_short(T, tpos, 2)) {
             emit(2u);
             emitted = true;
             n_hits += stat_inc;
@@ -324,7 +380,7 @@ struct Scanner {
       if (P.st.n1 && !(longest && emitted)) {
         const uint32_t k1 = gram >> 24;
         if ((P.st.bitmap1[k1 >> 5] >> (k1 & 31)) & 1u) {
-          if (end_ok_short(T, pos + 1, 1)) {
+          if (end_ok_short(T, tpos, 1)) {
             emit(1u);
             n_hits += stat_inc;
           } else {
@@ -335,15 +391,40 @@ struct Scanner {
     }
   }
 
+  // class prefilter: bit 7 of every byte of the result = byte is in the class
+  __device__ __forceinline__ uint32_t class_word(uint32_t w) const {
+    const uint32_t t = w & C.and4;
+    uint32_t in = (t + C.addlo0) & ~(t + C.addhi0);
+    if (C.two) in |= (t + C.addlo1) & ~(t + C.addhi1);
+    return in & ~w & 0x80808080u;
+  }
+  // bits 7,15,23,31 -> bits 0..3
+  static __device__ __forceinline__ uint32_t gather4(uint32_t m) { return __umulhi(m, 0x02040810u) & 0xFu; }
+
   // stage 1 for one lane: 16 positions -> candidate masks (bit k = position lpos + k)
-  __device__ __forceinline__ void stage1(const TileCtx &T, uint32_t lpos, uint32_t &cg, uint32_t &cp,
-                                         uint32_t &valid) const {
+  __device__ __forceinline__ void stage1(const TileCtx &T, uint32_t lpos, uint32_t &cg, uint32_t &cp) const {
     const uint8_t *src = T.sb + kTilePre + lpos;
     const uint4 v = *reinterpret_cast<const uint4 *>(src);
-    const uint32_t w4 = *reinterpret_cast<const uint32_t *>(src + 16);
-    const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
     cg = 0;
     cp = 0;
+    if (HAS_CLS) {
+      const uint2 nx = *reinterpret_cast<const uint2 *>(src + 16);
+      // bit i = byte lpos+i is in the class, i < 24
+      uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
+                   (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
+                   (gather4(class_word(nx.y)) << 20);
+      // bit i = bytes lpos+i .. lpos+i+run-1 are all in the class (run <= 8, i < 16)
+      uint32_t have = 1;
+      while (have * 2 <= C.run) {
+        a &= a >> have;
+        have *= 2;
+      }
+      if (have < C.run) a &= a >> (C.run - have);
+      cg = a & 0xFFFFu;
+      return;
+    }
+    const uint32_t w4 = *reinterpret_cast<const uint32_t *>(src + 16);
+    const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
@@ -356,27 +437,28 @@ struct Scanner {
         cp |= ((p23s[b >> 5] >> (b & 31)) & 1u) << k;
       }
     }
-    const unsigned long long lp = T.p0 + lpos;
-    valid = 0;
-    if (lp < T.end) valid = (T.end - lp >= 16) ? 0xFFFFu : ((1u << (uint32_t)(T.end - lp)) - 1u);
   }
 
   // One 512-byte chunk of a warp.  The warp's candidates are compacted into a queue in
   // position order; then every lane takes one candidate per sub-step, kProbeUnroll sub-steps
-  // are issued together (their slot loads overlap), and accepted matches are appended in
+  // are issued together (their bucket loads overlap), and accepted matches are appended in
   // candidate order (ballot + popc; a shuffle scan only when a position has several matches;
   // a position with more than four matches is evaluated a second time for the rest).
-  //   direct == false: matches go to `stage` (packed, shared memory, `cap` entries); when they
-  //                    do not fit, *overflow is set and the tile is redone with
-  //   direct == true : matches go to P.out[out_base ...] as final records.
-  // Returns the exact number of matches of the chunk in both modes.
+  //   kStageMode : matches go to `stage` (packed, shared memory, `cap` entries); when they
+  //                do not fit, *overflow is set (the tile goes on the redo list);
+  //   kCountMode : nothing is written;
+  //   kDirectMode: matches go to P.out[out_base ...] as final records.
+  // Returns the exact number of matches of the chunk in all modes.
   static constexpr int kProbeUnroll = 4;
+  template <int MODE>
   __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t *stage,
-                                                 uint32_t used, uint32_t cap, uint16_t *queue, bool direct,
+                                                 uint32_t used, uint32_t cap, uint16_t *queue,
                                                  unsigned long long out_base, unsigned long long emit_base,
                                                  const uint32_t *map, uint32_t *overflow) const {
-    uint32_t cg, cp, valid;
-    stage1(T, cbase + lane * 16, cg, cp, valid);
+    uint32_t cg, cp;
+    const uint32_t lpos = cbase + lane * 16;
+    stage1(T, lpos, cg, cp);
+    const uint32_t valid = lpos >= T.nscan ? 0u : (T.nscan - lpos >= 16 ? 0xFFFFu : ((1u << (T.nscan - lpos)) - 1u));
     uint32_t cand = (cg | cp) & valid;
     const uint32_t cnt = __popc(cand);
     uint32_t incl = cnt;
@@ -438,20 +520,22 @@ struct Scanner {
         }
         const uint32_t at = used + found + pre;
         auto put = [&](uint32_t i, uint32_t len) {
-          if (direct) {
+          if (MODE == kDirectMode) {
             const unsigned long long r = out_base + at + i;
             if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
-          } else if (at + i < cap && !(len >> kPackLenBits)) {
-            stage[at + i] = (tpos << kPackLenBits) | len;
-          } else {
-            *overflow = 1;
+          } else if (MODE == kStageMode) {
+            if (at + i < cap && !(len >> kPackLenBits)) {
+              stage[at + i] = (tpos << kPackLenBits) | len;
+            } else {
+              *overflow = 1;
+            }
           }
         };
         if (n > 0) put(0, m0);
         if (n > 1) put(1, m1);
         if (n > 2) put(2, m2);
         if (n > 3) put(3, m3);
-        if (many && __any_sync(kFull, n > 4)) {
+        if (MODE != kCountMode && many && __any_sync(kFull, n > 4)) {
           if (n > 4) { // evaluate the position again for matches 5, 6, ...
             uint32_t i = 0;
             stat_inc = 0;
@@ -482,150 +566,178 @@ struct Scanner {
     *reinterpret_cast<unsigned long long *>(&o->len) = (unsigned long long)len;
     o->ptr = P.match_ptr_base + off;
   }
+
+  __device__ __forceinline__ void flush_stats(uint32_t lane) const {
+    unsigned long long h = n_hits, mi = n_miss, cm = n_cmp, lh = n_long_hits;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      h += __shfl_xor_sync(kFull, h, d);
+      mi += __shfl_xor_sync(kFull, mi, d);
+      cm += __shfl_xor_sync(kFull, cm, d);
+      lh += __shfl_xor_sync(kFull, lh, d);
+    }
+    if (lane == 0 && P.counters) {
+      if (h) atomicAdd(P.counters + 0, h);
+      if (mi) atomicAdd(P.counters + 1, mi);
+      if (cm) atomicAdd(P.counters + 2, cm);
+      if (lh) atomicAdd(P.counters + 3, lh);
+    }
+  }
 };
 
+// Fills `I` for launch-local tile t and starts its bulk copy into `dst` (a stage buffer).
+__device__ __forceinline__ void start_tile(const ScanParams &P, uint32_t t, StageInfo &I, uint8_t *dst, uint64_t *bar) {
+  I.tile = t;
+  uint32_t win = 0;
+  if (P.flags & kWindowMode) {
+    win = t / P.tiles_per_win;
+    const WindowDesc wd = P.windows[win];
+    I.p0 = (unsigned long long)(t % P.tiles_per_win) * kTileBytes;
+    I.len = wd.norm_len;
+    I.end = wd.norm_len;
+    I.boff = (long long)(P.win_buf_off + (unsigned long long)win * P.win_stride + I.p0);
+    I.tail = wd.tail;
+    I.emit_base = P.win_src_base + (unsigned long long)win * kWindowBytes;
+  } else {
+    I.p0 = P.scan_begin + (unsigned long long)t * kTileBytes;
+    I.len = P.seg_len;
+    I.end = P.scan_end < P.seg_len ? P.scan_end : P.seg_len;
+    I.boff = P.seg_buf_off + (long long)I.p0;
+    I.tail = P.tail_byte;
+    I.emit_base = 0;
+  }
+  I.win = win;
+  I.staged = 0;
+  if (I.p0 < I.end) {
+    const long long pre = I.boff >= kTilePre ? kTilePre : 0;
+    long long e = I.boff + kTileBytes + kTileHalo;
+    if (e > (long long)P.buf_len) e = (long long)P.buf_len;
+    const uint32_t bytes = (uint32_t)(e - (I.boff - pre));
+    I.staged = (uint32_t)(e - I.boff);
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(dst + (kTilePre - pre), P.buf + (I.boff - pre), bytes, bar);
+  } else {
+    mbar_expect_tx(bar, 0); // empty tile: the phase completes at once
+  }
+}
+
+__device__ __forceinline__ void tile_ctx(const StageInfo &I, const uint8_t *sb, TileCtx &T) {
+  T.sb = sb;
+  T.p0 = I.p0;
+  T.boff = I.boff;
+  const unsigned long long left = I.len - I.p0;
+  T.rem0 = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;
+  const unsigned long long ns = I.end > I.p0 ? I.end - I.p0 : 0;
+  T.nscan = ns > (unsigned long long)kTileBytes ? (uint32_t)kTileBytes : (uint32_t)ns;
+  T.staged = I.staged;
+  T.tail = I.tail;
+  T.first = I.p0 == 0;
+}
+
+struct SmemLayout {
+  SmemHeader *H;
+  uint8_t *ring;
+  uint32_t *g4s, *p23s, *staging;
+  uint16_t *queues;
+};
 template <bool HAS_G4, bool HAS_P23>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t S = P.stages;
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem);                        // [3]
-  uint32_t *s_ovf = reinterpret_cast<uint32_t *>(smem + 24);                  // [2]
-  unsigned long long *s_excl = reinterpret_cast<unsigned long long *>(smem + 32);
-  uint32_t *s_wcnt = reinterpret_cast<uint32_t *>(smem + 40);                 // [16]
-  uint32_t *s_wpre = reinterpret_cast<uint32_t *>(smem + 104);                // [16]
-  StageInfo *s_info = reinterpret_cast<StageInfo *>(smem + 256);              // [3] x 64 B
-  uint8_t *ring = smem + 256 + 3 * 64 + 64;                                   // 512: 128-aligned
-  uint32_t *g4s = reinterpret_cast<uint32_t *>(ring + S * kStageBytes);
-  uint32_t *p23s = g4s + (HAS_G4 ? P.st.g4_words : 0);
-  uint32_t *staging = p23s + (HAS_P23 ? P.st.p23_words : 0);
-  uint16_t *queues = reinterpret_cast<uint16_t *>(staging + kScanWarps * P.stage_cap);
-
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t fl = P.flags;
-  const bool window_mode = fl & kWindowMode;
-
-  // ---- filters into shared memory
+__device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, uint32_t stages, uint32_t staging_words) {
+  SmemLayout L;
+  L.H = reinterpret_cast<SmemHeader *>(smem);
+  L.ring = smem + kSmemHeader;
+  L.g4s = reinterpret_cast<uint32_t *>(L.ring + (size_t)stages * kStageBytes);
+  L.p23s = L.g4s + (HAS_G4 ? P.st.g4_words : 0);
+  L.staging = L.p23s + (HAS_P23 ? P.st.p23_words : 0);
+  L.queues = reinterpret_cast<uint16_t *>(L.staging + staging_words);
+  return L;
+}
+template <bool HAS_G4, bool HAS_P23>
+__device__ __forceinline__ void load_filters(const SmemLayout &L, const ScanParams &P, uint32_t tid, uint32_t nthreads) {
   if (HAS_G4) {
     const uint4 *src = reinterpret_cast<const uint4 *>(P.st.g4);
-    uint4 *dst = reinterpret_cast<uint4 *>(g4s);
-    for (uint32_t i = tid; i < P.st.g4_words / 4; i += kScanThreads) dst[i] = __ldg(src + i);
+    uint4 *dst = reinterpret_cast<uint4 *>(L.g4s);
+    for (uint32_t i = tid; i < P.st.g4_words / 4; i += nthreads) dst[i] = __ldg(src + i);
   }
   if (HAS_P23) {
     const uint4 *src = reinterpret_cast<const uint4 *>(P.st.p23);
-    uint4 *dst = reinterpret_cast<uint4 *>(p23s);
-    for (uint32_t i = tid; i < P.st.p23_words / 4; i += kScanThreads) dst[i] = __ldg(src + i);
+    uint4 *dst = reinterpret_cast<uint4 *>(L.p23s);
+    for (uint32_t i = tid; i < P.st.p23_words / 4; i += nthreads) dst[i] = __ldg(src + i);
   }
+}
+
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t S = P.stages;
+  const uint32_t cap = P.stage_cap;
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, 2u * kScanWarps * cap);
+  SmemHeader &H = *L.H;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t fl = P.flags;
+
+  load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
   if (tid == 0) {
-    for (uint32_t s = 0; s < S; ++s) mbar_init(&full[s], 1);
-    s_ovf[0] = s_ovf[1] = 0;
+    for (uint32_t s = 0; s < kMaxStages; ++s) {
+      mbar_init(&H.full[s], 1);
+      mbar_init(&H.scanned[s], kScanWarps);
+    }
+    mbar_init(&H.ready[0], 1);
+    mbar_init(&H.ready[1], 1);
+    H.ovf[0] = H.ovf[1] = 0;
+    H.ovf_final[0] = H.ovf_final[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // The producer thread takes the next ticket and starts the bulk copy of that tile.
-  auto produce = [&](uint32_t s) {
-    const uint32_t t = atomicAdd(P.ticket, 1u);
-    StageInfo &I = s_info[s];
-    I.tile = t;
-    if (t >= P.num_tiles) return;
-    uint32_t win = 0;
-    if (window_mode) {
-      win = t / P.tiles_per_win;
-      const WindowDesc wd = P.windows[win];
-      I.p0 = (unsigned long long)(t % P.tiles_per_win) * kTileBytes;
-      I.len = wd.norm_len;
-      I.end = wd.norm_len;
-      I.boff = (long long)(P.win_buf_off + (unsigned long long)win * P.win_stride + I.p0);
-      I.tail = wd.tail;
-      I.emit_base = P.win_src_base + (unsigned long long)win * kWindowBytes;
-    } else {
-      I.p0 = P.scan_begin + (unsigned long long)t * kTileBytes;
-      I.len = P.seg_len;
-      I.end = P.scan_end < P.seg_len ? P.scan_end : P.seg_len;
-      I.boff = P.seg_buf_off + (long long)I.p0;
-      I.tail = P.tail_byte;
-      I.emit_base = 0;
-    }
-    I.win = win;
-    uint32_t bytes = 0;
-    I.staged = 0;
-    if (I.p0 < I.end) {
-      const long long pre = I.boff >= kTilePre ? kTilePre : 0;
-      long long e = I.boff + kTileBytes + kTileHalo;
-      if (e > (long long)P.buf_len) e = (long long)P.buf_len;
-      bytes = (uint32_t)(e - (I.boff - pre));
-      I.staged = (uint32_t)(e - I.boff);
-      mbar_expect_tx(&full[s], bytes);
-      tma_load_1d(ring + (size_t)s * kStageBytes + (kTilePre - pre), P.buf + (I.boff - pre), bytes, &full[s]);
-    } else {
-      mbar_expect_tx(&full[s], 0); // empty tile: the phase completes at once
-    }
-  };
-  if (tid == 32)
-    for (uint32_t s = 0; s < S; ++s) produce(s);
-  __syncthreads();
-
-  Scanner<HAS_G4, HAS_P23> sc{P, g4s, p23s, fl};
-  const uint32_t cap = P.stage_cap;
-  uint32_t *my_stage = staging + warp * cap;
-  uint16_t *my_queue = queues + warp * kChunkBytes;
-
-  for (uint32_t k = 0;; ++k) {
-    const uint32_t s = k % S;
-    const StageInfo &I = s_info[s];
-    const uint32_t tile = *reinterpret_cast<const volatile uint32_t *>(&I.tile);
-    if (tile >= P.num_tiles) break;
-    mbar_wait(&full[s], (k / S) & 1u);
-
-    TileCtx T;
-    T.sb = ring + (size_t)s * kStageBytes;
-    T.p0 = I.p0;
-    T.len = I.len;
-    T.end = I.end;
-    T.boff = I.boff;
-    T.staged = I.staged;
-    T.tail = I.tail;
-    const unsigned long long emit_base = I.emit_base;
-    const uint32_t *map =
-        (window_mode && !(fl & kIdentityMap)) ? P.map + (size_t)I.win * kWindowBytes : nullptr;
-    uint32_t *ovf = &s_ovf[k & 1];
-
-    // ---- scan this warp's 2 KiB of the tile
-    uint32_t wc = 0;
-    for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
-      const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
-      if (T.p0 + cbase >= T.end) break;
-      wc += sc.scan_chunk(T, cbase, lane, my_stage, wc, cap, my_queue, false, 0, emit_base, map, ovf);
-    }
-    if (lane == 0) s_wcnt[warp] = wc;
-    __syncthreads(); // (A) tile evaluated, counts visible
-
-    const bool overflow = *reinterpret_cast<volatile uint32_t *>(ovf) != 0;
-    if (tid == 32) {
-      s_ovf[(k + 1) & 1] = 0;
-      if (!overflow) produce(s); // stage buffer is free again
-    }
-    if (warp == 0) {
+  if (warp == kScanWarps) {
+    // ================= control warp: TMA producer + decoupled look-back =================
+    auto produce = [&](uint32_t s) { // lane 0 only
+      const uint32_t t = atomicAdd(P.ticket, 1u);
+      StageInfo &I = H.info[s];
+      if (t >= P.num_tiles) {
+        I.tile = kNoTile;
+        mbar_expect_tx(&H.full[s], 0);
+        return;
+      }
+      start_tile(P, t, I, L.ring + (size_t)s * kStageBytes, &H.full[s]);
+    };
+    if (lane == 0)
+      for (uint32_t s = 0; s < S; ++s) produce(s);
+    __syncwarp();
+    uint32_t s = 0, ph = 0;
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t tile = *reinterpret_cast<const volatile uint32_t *>(&H.info[s].tile);
+      __syncwarp(); // every lane has read the stage info before lane 0 refills the stage
+      if (tile == kNoTile) break;
+      mbar_wait(&H.scanned[s], ph);
+      const uint32_t b = k & 1;
+      if (lane == 0) {
+        H.tout[b].p0 = H.info[s].p0;
+        H.tout[b].emit_base = H.info[s].emit_base;
+        H.tout[b].win = H.info[s].win;
+        produce(s); // the stage buffer is free again
+      }
       // warp totals -> exclusive prefixes; then the decoupled look-back for the tile base
-      uint32_t c = lane < kScanWarps ? s_wcnt[lane] : 0, incl = c;
+      uint32_t c = lane < kScanWarps ? H.wcnt[b][lane] : 0, incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(kFull, incl, d);
         if (lane >= (uint32_t)d) incl += t;
       }
-      if (lane < kScanWarps) s_wpre[lane] = incl - c;
+      if (lane < kScanWarps) H.wpre[b][lane] = incl - c;
       const unsigned long long tile_total = __shfl_sync(kFull, incl, 31);
       const long long g = (long long)P.tile_base + tile;
       unsigned long long excl = 0;
       if (g > 0) {
-        if (lane == 0) st_release(P.tile_state + g, kStateAggregate | tile_total);
+        if (lane == 0) st_relaxed(P.tile_state + g, kStateAggregate | tile_total);
         long long j = g - 1;
         while (true) {
           const long long mine = j - lane;
           unsigned long long v = kStatePrefix; // virtual predecessor of tile 0: prefix 0
           if (mine >= 0) {
             do {
-              v = ld_acquire(P.tile_state + mine);
+              v = ld_relaxed(P.tile_state + mine);
             } while ((v >> 62) == 0);
           }
           const uint32_t is_prefix = __ballot_sync(kFull, (v >> 62) == 2);
@@ -639,72 +751,165 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
         }
       }
       if (lane == 0) {
-        st_release(P.tile_state + g, kStatePrefix | (excl + tile_total));
-        *s_excl = excl;
+        st_relaxed(P.tile_state + g, kStatePrefix | (excl + tile_total));
+        H.base[b] = excl;
         if (tile == P.num_tiles - 1) *P.total = excl + tile_total;
+        const uint32_t ovf = H.ovf[b];
+        H.ovf_final[b] = ovf;
+        H.ovf[b] = 0;
+        if (ovf) P.redo_list[atomicAdd(P.redo_count, 1u)] = tile;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&H.ready[b]);
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
       }
     }
-    __syncthreads(); // (B) tile base known
+    return;
+  }
 
-    const unsigned long long base = *s_excl + s_wpre[warp];
-    if (!overflow) {
-      for (uint32_t i = lane; i < wc; i += 32) {
-        const uint32_t e = my_stage[i];
-        const unsigned long long r = base + i;
-        if (r < P.out_cap) sc.write_record(r, emit_base, T.p0 + (e >> kPackLenBits), e & ((1u << kPackLenBits) - 1), map);
+  // ================================ scanning warps ================================
+  Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
+  uint16_t *my_queue = L.queues + warp * kChunkBytes;
+  const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
+
+  auto copy_out = [&](uint32_t j, uint32_t wc) { // tile iteration j, this warp's staged matches
+    const uint32_t b = j & 1;
+    mbar_wait(&H.ready[b], (j >> 1) & 1u);
+    if (H.ovf_final[b]) return; // the redo pass writes this tile
+    const unsigned long long base = H.base[b] + H.wpre[b][warp];
+    const TileOut to = H.tout[b];
+    const uint32_t *map = use_map ? P.map + (size_t)to.win * kWindowBytes : nullptr;
+    const uint32_t *st = L.staging + ((size_t)b * kScanWarps + warp) * cap;
+    for (uint32_t i = lane; i < wc; i += 32) {
+      const uint32_t e = st[i];
+      const unsigned long long r = base + i;
+      if (r < P.out_cap) sc.write_record(r, to.emit_base, to.p0 + (e >> kPackLenBits), e & ((1u << kPackLenBits) - 1), map);
+    }
+  };
+
+  uint32_t s = 0, ph = 0, prev_wc = 0, k = 0;
+  for (;; ++k) {
+    mbar_wait(&H.full[s], ph);
+    const StageInfo &I = H.info[s];
+    if (I.tile == kNoTile) break;
+    TileCtx T;
+    tile_ctx(I, L.ring + (size_t)s * kStageBytes, T);
+    const uint32_t b = k & 1;
+    uint32_t *my_stage = L.staging + ((size_t)b * kScanWarps + warp) * cap;
+
+    uint32_t wc = 0;
+    for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
+      const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
+      if (cbase >= T.nscan) break;
+      wc += sc.template scan_chunk<kStageMode>(T, cbase, lane, my_stage, wc, cap, my_queue, 0, 0, nullptr, &H.ovf[b]);
+    }
+    if (lane == 0) H.wcnt[b][warp] = wc;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&H.scanned[s]);
+    if (k > 0) copy_out(k - 1, prev_wc);
+    prev_wc = wc;
+    if (++s == S) {
+      s = 0;
+      ph ^= 1;
+    }
+  }
+  if (k > 0) copy_out(k - 1, prev_wc);
+  sc.flush_stats(lane);
+}
+
+// Tiles of the redo list, one CTA per tile at a time: count per warp, prefix, then evaluate
+// again writing final records.  The tile's base is the inclusive prefix of its predecessor.
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
+__global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_constant__ ScanParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, 1, 0);
+  SmemHeader &H = *L.H;
+  const uint32_t n = *P.redo_count;
+  if (blockIdx.x >= n) return;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t fl = P.flags;
+  load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
+  if (tid == 0) {
+    mbar_init(&H.full[0], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
+  uint16_t *my_queue = L.queues + (warp % kScanWarps) * kChunkBytes;
+  const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
+  uint32_t ph = 0;
+  for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+    const uint32_t tile = P.redo_list[e];
+    if (tid == 0) start_tile(P, tile, H.info[0], L.ring, &H.full[0]);
+    mbar_wait(&H.full[0], ph);
+    ph ^= 1;
+    TileCtx T;
+    tile_ctx(H.info[0], L.ring, T);
+    const unsigned long long emit_base = H.info[0].emit_base;
+    const uint32_t *map = use_map ? P.map + (size_t)H.info[0].win * kWindowBytes : nullptr;
+    uint32_t wc = 0;
+    if (warp < kScanWarps) {
+      for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
+        const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
+        if (cbase >= T.nscan) break;
+        sc.stat_inc = 0;
+        wc += sc.template scan_chunk<kCountMode>(T, cbase, lane, nullptr, wc, 0, my_queue, 0, 0, nullptr, nullptr);
+        sc.stat_inc = 1;
       }
-    } else {
-      // rare: staging overflowed somewhere in this tile -> evaluate again, straight to HBM
-      uint32_t dummy = 0;
+      if (lane == 0) H.wcnt[0][warp] = wc;
+    }
+    __syncthreads();
+    if (warp < kScanWarps) {
+      unsigned long long base = 0;
+      const long long g = (long long)P.tile_base + tile;
+      if (g > 0) base = P.tile_state[g - 1] & kStateValueMask;
+      for (uint32_t w = 0; w < warp; ++w) base += H.wcnt[0][w];
       uint32_t done = 0;
       for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
         const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
-        if (T.p0 + cbase >= T.end) break;
-        done += sc.scan_chunk(T, cbase, lane, my_stage, done, cap, my_queue, true, base, emit_base, map, &dummy);
+        if (cbase >= T.nscan) break;
+        sc.stat_inc = 0; // the main pass has counted this tile already
+        done += sc.template scan_chunk<kDirectMode>(T, cbase, lane, nullptr, done, 0, my_queue, base, emit_base, map, nullptr);
+        sc.stat_inc = 1;
       }
-      __syncthreads();
-      if (tid == 32) produce(s);
     }
-    __syncwarp();
-  }
-
-  // statistics: one atomic per warp and counter
-  unsigned long long h = sc.n_hits, mi = sc.n_miss, cm = sc.n_cmp, lh = sc.n_long_hits;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    h += __shfl_xor_sync(kFull, h, d);
-    mi += __shfl_xor_sync(kFull, mi, d);
-    cm += __shfl_xor_sync(kFull, cm, d);
-    lh += __shfl_xor_sync(kFull, lh, d);
-  }
-  if (lane == 0 && P.counters) {
-    if (h) atomicAdd(P.counters + 0, h);
-    if (mi) atomicAdd(P.counters + 1, mi);
-    if (cm) atomicAdd(P.counters + 2, cm);
-    if (lh) atomicAdd(P.counters + 3, lh);
+    __syncthreads(); // the stage buffer and wcnt are reused by the next entry
   }
 }
 
-template <bool G, bool Q>
-cudaError_t launch_variant(const ScanParams &p, int grid, size_t smem, cudaStream_t stream) {
-  scan_kernel<G, Q><<<grid, kScanThreads, smem, stream>>>(p);
+template <bool G, bool Q, bool C>
+cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
+  const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
+  scan_kernel<G, Q, C><<<grid, kScanThreads, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, 1, 0), stream>>>(p);
   return cudaGetLastError();
+}
+
+template <bool G, bool Q, bool C>
+cudaError_t configure_variant(size_t smem_limit) {
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(redo_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
 }
 
 } // namespace
 
 size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t stage_cap) {
-  return 512 + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 +
-         size_t(kScanWarps) * stage_cap * 4 + kQueueBytes;
+  return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 +
+         size_t(2) * kScanWarps * stage_cap * 4 + kQueueBytes;
 }
 
 uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *stage_cap) {
-  for (uint32_t s = 3; s >= 2; --s) {
+  for (uint32_t s = kMaxStages; s >= 2; --s) {
     if (scan_smem_bytes(st, s, kStageCapMin) > smem_limit) continue;
     // whatever shared memory is left goes to the staging areas (denser matches before a tile
     // has to be redone)
     const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
-    uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~31u;
+    uint32_t cap = uint32_t(spare / (size_t(2) * kScanWarps * 4)) & ~31u;
     if (cap > kStageCapMax) cap = kStageCapMax;
     *stage_cap = cap;
     return s;
@@ -714,20 +919,22 @@ uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *st
 
 cudaError_t scan_configure(size_t smem_limit) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit)) != cudaSuccess) return e;
-  return cudaSuccess;
+  if ((e = configure_variant<true, true, false>(smem_limit)) != cudaSuccess) return e;
+  if ((e = configure_variant<true, false, false>(smem_limit)) != cudaSuccess) return e;
+  if ((e = configure_variant<true, false, true>(smem_limit)) != cudaSuccess) return e;
+  if ((e = configure_variant<false, true, false>(smem_limit)) != cudaSuccess) return e;
+  return configure_variant<false, false, false>(smem_limit);
 }
 
-cudaError_t scan_launch(const ScanParams &p, int grid, cudaStream_t stream) {
+cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches) {
   const size_t smem = scan_smem_bytes(p.st, p.stages, p.stage_cap);
-  const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0;
-  if (g && q) return launch_variant<true, true>(p, grid, smem, stream);
-  if (g) return launch_variant<true, false>(p, grid, smem, stream);
-  if (q) return launch_variant<false, true>(p, grid, smem, stream);
-  return launch_variant<false, false>(p, grid, smem, stream);
+  const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0, c = g && !q && p.st.cls.run != 0;
+  if (launches) *launches += 2;
+  if (g && q) return launch_variant<true, true, false>(p, sms, smem, stream);
+  if (c) return launch_variant<true, false, true>(p, sms, smem, stream);
+  if (g) return launch_variant<true, false, false>(p, sms, smem, stream);
+  if (q) return launch_variant<false, true, false>(p, sms, smem, stream);
+  return launch_variant<false, false, false>(p, sms, smem, stream);
 }
 
 } // namespace olm

@@ -1,4 +1,4 @@
-// scan.cuh -- launch interface of the scan kernel (scan.cu) and the record layout in HBM.
+// scan.cuh -- launch interface of the scan kernels (scan.cu) and the record layout in HBM.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,57 +38,62 @@ enum ScanFlags : uint32_t {
 };
 
 // Geometry of the kernel (compile-time; DESIGN.md "scan kernel").
-constexpr int kScanThreads = 512;
-constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kTileBytes = 32768;                 // positions per tile
-constexpr int kTilePre = 16;                      // bytes staged in front of a tile (previous byte)
-constexpr int kTileHalo = 112;                    // bytes staged behind a tile
-constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 32896 = 257*128
-constexpr int kWarpSpan = kTileBytes / kScanWarps; // 2048 positions per warp and tile
-constexpr int kChunkBytes = 512;                  // 32 lanes x 16 bytes
-constexpr uint32_t kStageCapMin = 256;            // staged matches per warp and tile: at least ...
-constexpr uint32_t kStageCapMax = 2048;           // ... at most (= one per position of the warp's span)
-constexpr int kQueueBytes = kScanWarps * kChunkBytes * 2; // per-warp candidate queue (u16 entries)
-constexpr int kSmemFixed = 256;
-constexpr uint32_t kPackLenBits = 17;             // staged entry = pos_in_tile << 17 | len
+constexpr int kScanWarps = 16;                      // warps that scan
+constexpr int kScanThreads = (kScanWarps + 1) * 32; // + one control warp (TMA producer, look-back)
+constexpr int kTileBytes = 16384;                   // positions per tile
+constexpr int kTilePre = 16;                        // bytes staged in front of a tile (previous byte)
+constexpr int kTileHalo = 112;                      // bytes staged behind a tile
+constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 16512 = 129*128
+constexpr int kWarpSpan = kTileBytes / kScanWarps;  // 1024 positions per warp and tile
+constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes
+constexpr int kMaxStages = 4;
+constexpr uint32_t kStageCapMin = 64;               // staged matches per warp and tile: at least ...
+constexpr uint32_t kStageCapMax = 1024;             // ... at most
+constexpr int kQueueBytes = kScanWarps * kChunkBytes * 2; // candidate queue: u16 per position of a chunk
+constexpr int kSmemHeader = 1024;                   // barriers, per-tile bookkeeping, stage infos
+constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
 
 struct ScanParams {
   DeviceStore st;
   // input bytes
-  const uint8_t *buf;    // 16-byte aligned device buffer
-  uint64_t buf_len;      // readable bytes (a multiple of 16)
-  int64_t seg_buf_off;   // plain/shard mode: buffer offset of segment position 0 (may be negative)
-  uint64_t seg_len;      // plain/shard mode: length of the whole haystack (global N)
-  uint64_t scan_begin;   // first owned start position (multiple of 16)
-  uint64_t scan_end;     // one past the last owned start position
-  uint32_t tail_byte;    // value assumed at position seg_len (plain mode)
+  const uint8_t *buf;  // 16-byte aligned device buffer
+  uint64_t buf_len;    // readable bytes (a multiple of 16)
+  int64_t seg_buf_off; // plain/shard mode: buffer offset of segment position 0 (may be negative)
+  uint64_t seg_len;    // plain/shard mode: length of the whole haystack (global N)
+  uint64_t scan_begin; // first owned start position (multiple of 16)
+  uint64_t scan_end;   // one past the last owned start position
+  uint32_t tail_byte;  // value assumed at position seg_len (plain mode)
   // window mode
   const WindowDesc *windows;
-  const uint32_t *map;     // per window: kWindowBytes entries, normalised index -> source index
-  uint64_t win_stride;     // bytes between normalised windows in buf
-  uint64_t win_buf_off;    // buffer offset of window 0
-  uint64_t win_src_base;   // source offset of window 0 (global)
+  const uint32_t *map;   // per window: kWindowBytes entries, normalised index -> source index
+  uint64_t win_stride;   // bytes between normalised windows in buf
+  uint64_t win_buf_off;  // buffer offset of window 0
+  uint64_t win_src_base; // source offset of window 0 (global)
   uint32_t tiles_per_win;
   // tiles
-  uint32_t num_tiles;      // tiles of this launch
-  uint32_t tile_base;      // global index of this launch's first tile in tile_state[]
+  uint32_t num_tiles;             // tiles of this launch
+  uint32_t tile_base;             // global index of this launch's first tile in tile_state[]
   unsigned long long *tile_state; // decoupled look-back descriptors
-  unsigned int *ticket;    // dynamic tile counter of this launch
+  unsigned int *ticket;           // dynamic tile counter of this launch
+  // tiles whose matches did not fit the staging area; rewritten by redo_kernel
+  uint32_t *redo_list;     // launch-local tile indices
+  unsigned int *redo_count;
   // output
   Record *out;
   uint64_t out_cap;
   uint64_t match_ptr_base;
-  unsigned long long *total; // inclusive count after the last tile of this launch
-  unsigned long long *counters; // [0] long-path attempts that found a bucket, ... (see engine)
+  unsigned long long *total;    // inclusive count after the last tile of this launch
+  unsigned long long *counters; // hits, misses, comparisons, long hits (omega_match_stats_t)
   uint32_t flags;
-  uint32_t stages;         // ring depth (2 or 3)
-  uint32_t stage_cap;      // staged matches per warp and tile
+  uint32_t stages;    // ring depth
+  uint32_t stage_cap; // staged matches per warp and tile (two buffers of this size per warp)
 };
 
 size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t stage_cap);
 // chooses the deepest ring that fits (and the staging capacity); returns 0 if the filters do not fit at all
 uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *stage_cap);
-cudaError_t scan_launch(const ScanParams &p, int grid, cudaStream_t stream);
+// main pass followed by the redo pass (which exits at once when no tile overflowed)
+cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches);
 cudaError_t scan_configure(size_t smem_limit);
 
 } // namespace olm

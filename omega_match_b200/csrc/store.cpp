@@ -124,56 +124,69 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
   s->store.assign(size_t(h.store_bytes) + 16, 0);
   if (h.store_bytes) std::memcpy(s->store.data(), v.patterns, size_t(h.store_bytes));
 
-  // ---- slots: bucket grams first, then the 4-byte patterns are merged in
+  // ---- keys + slots: bucket grams first, then the 4-byte patterns are merged in
   const uint64_t n_keys_upper = buckets.size() + uint64_t(v.n4);
-  // buckets of two slots; capacity >= 2x the keys (4x while the table stays small)
+  // buckets of four places; #buckets >= #keys, i.e. load <= 0.25 (see device_tables.h)
   uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, n_keys_upper)));
-  if (n_keys_upper <= (1u << 18)) ++lg_buckets;
-  if (lg_buckets > 29) return "too many distinct grams";
-  const uint32_t n_slots = 2u << lg_buckets;
+  if (lg_buckets > 27) return "too many distinct grams";
+  const uint32_t n_buckets = 1u << lg_buckets;
   DeviceStore &d = s->params;
-  d.slot_shift = 32 - lg_buckets;
-  d.slot_mask = (1u << lg_buckets) - 1;
-  s->slots.assign(n_slots, Slot{0, 0, 0, 0});
+  d.key_shift = 32 - lg_buckets;
+  d.key_mask = n_buckets - 1;
+  {
+    // a value no gram of the store equals marks unused places
+    std::vector<uint32_t> all;
+    all.reserve(n_keys_upper);
+    for (const BucketRef &b : buckets) all.push_back(b.gram);
+    for (uint32_t i = 0; i < v.n4; ++i) all.push_back(rd32(v.arr4 + 4ull * i));
+    std::sort(all.begin(), all.end());
+    uint32_t e = 0xFFFFFFFFu;
+    while (std::binary_search(all.begin(), all.end(), e)) --e;
+    d.empty_key = e;
+  }
+  s->keys.assign(n_buckets, make_uint4(d.empty_key, d.empty_key, d.empty_key, d.empty_key));
+  s->slots.assign(size_t(n_buckets) * 4, Slot{0, 0, 0, 0});
   s->recs.reserve(n_recs_multi);
 
-  auto next4_of = [&](uint64_t off, uint32_t len) {
+  auto word_of = [&](uint64_t off, uint32_t len, uint32_t from) {
     uint32_t w = 0;
-    const uint32_t m = std::min<uint32_t>(len - 4, 4);
-    for (uint32_t i = 0; i < m; ++i) w |= uint32_t(s->store[off + 4 + i]) << (8 * i);
+    for (uint32_t i = 0; i < 4 && from + i < len; ++i) w |= uint32_t(s->store[off + from + i]) << (8 * i);
     return w;
   };
-  auto find_or_claim = [&](uint32_t gram) -> Slot & {
-    for (uint32_t b = slot_home(d, gram);; b = (b + 1) & d.slot_mask) {
-      for (uint32_t k = 0; k < 2; ++k) {
-        Slot &sl = s->slots[2 * size_t(b) + k];
-        if (sl.meta == 0 || sl.key == gram) {
-          sl.key = gram;
-          return sl;
+  // returns the slot of `gram`, claiming the first free place from its home bucket on
+  auto find_or_claim = [&](uint32_t gram, bool *fresh) -> Slot & {
+    for (uint32_t b = key_home(d, gram);; b = (b + 1) & d.key_mask) {
+      uint32_t *k = reinterpret_cast<uint32_t *>(&s->keys[b]);
+      for (uint32_t j = 0; j < 4; ++j) {
+        if (k[j] == gram || k[j] == d.empty_key) {
+          *fresh = k[j] != gram;
+          k[j] = gram;
+          return s->slots[4 * size_t(b) + j];
         }
       }
     }
   };
   uint32_t n_keys = 0;
   for (const BucketRef &b : buckets) {
-    Slot &sl = find_or_claim(b.gram);
-    if (sl.meta != 0) return "gram appears in two buckets";
+    bool fresh = false;
+    Slot &sl = find_or_claim(b.gram, &fresh);
+    if (!fresh) return "gram appears in two buckets";
     ++n_keys;
     if (b.count == 1) {
       const uint64_t po = rd64(b.recs);
       const uint32_t pl = rd32(b.recs + 8);
       sl.meta = pl;
       sl.ref = uint32_t(po);
-      sl.next4 = next4_of(po, pl);
+      sl.next4 = word_of(po, pl, 4);
+      sl.next8 = word_of(po, pl, 8);
     } else {
       sl.meta = kSlotMulti | b.count;
       sl.ref = uint32_t(s->recs.size());
-      sl.next4 = 0;
       const size_t first = s->recs.size();
       for (uint32_t j = 0; j < b.count; ++j) {
         const uint64_t po = rd64(b.recs + 16ull * j);
         const uint32_t pl = rd32(b.recs + 16ull * j + 8);
-        s->recs.push_back(Rec{next4_of(po, pl), pl, uint32_t(po), 0});
+        s->recs.push_back(Rec{word_of(po, pl, 4), pl, uint32_t(po), word_of(po, pl, 8)});
       }
       // the scan emits a bucket's matches in record order and relies on "longest first"
       // (compiler.c:271 sorts the bucket that way; enforce it for foreign writers)
@@ -181,9 +194,9 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     }
   }
   for (uint32_t i = 0; i < v.n4; ++i) {
-    const uint32_t gram = rd32(v.arr4 + 4ull * i);
-    Slot &sl = find_or_claim(gram);
-    if (sl.meta == 0) ++n_keys;
+    bool fresh = false;
+    Slot &sl = find_or_claim(rd32(v.arr4 + 4ull * i), &fresh);
+    if (fresh) ++n_keys;
     sl.meta |= kSlotShort4;
   }
   s->n_keys = n_keys;
@@ -195,11 +208,12 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     d.g4_shift = 32 - lg;
     d.g4_words = (1u << lg) / 32;
     s->g4.assign(d.g4_words, 0);
-    for (const Slot &sl : s->slots)
-      if (sl.meta) {
-        const uint32_t b = g4_bit(d, sl.key);
-        s->g4[b >> 5] |= 1u << (b & 31);
-      }
+    for (const uint4 &kb : s->keys)
+      for (uint32_t k : {kb.x, kb.y, kb.z, kb.w})
+        if (k != d.empty_key) {
+          const uint32_t b = g4_bit(d, k);
+          s->g4[b >> 5] |= 1u << (b & 31);
+        }
   }
 
   // ---- p23: candidates for the 1..3 byte patterns
@@ -256,6 +270,75 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     if (v.bitmap2) std::memcpy(s->bitmap2.data(), v.bitmap2, 8192);
     if (v.bitmap1) std::memcpy(d.bitmap1, v.bitmap1, 32);
   }
+  // ---- byte-class prefilter (device_tables.h): only when every pattern has >= 4 bytes
+  if (v.n1 == 0 && v.n2 == 0 && v.n3 == 0 && (n_long || v.n4)) {
+    uint32_t run = v.n4 ? 4 : std::min<uint32_t>(8, h.smallest);
+    if (run == 7) run = 6;
+    bool used[256] = {false};
+    for (const BucketRef &b : buckets)
+      for (uint32_t j = 0; j < b.count; ++j) {
+        const uint64_t po = rd64(b.recs + 16ull * j);
+        for (uint32_t i = 0; i < run; ++i) used[v.patterns[po + i]] = true;
+      }
+    for (uint32_t i = 0; i < v.n4; ++i) {
+      const uint32_t g = rd32(v.arr4 + 4ull * i);
+      for (uint32_t k = 0; k < 4; ++k) used[(g >> (8 * k)) & 0xFF] = true;
+    }
+    bool ascii = true;
+    for (uint32_t b = 0x80; b < 256; ++b) ascii = ascii && !used[b];
+    if (ascii && run >= 4) {
+      // best cover of the used values by <= 2 ranges, with and without folding bit 5
+      ByteClass best;
+      uint32_t best_cost = 1u << 30;
+      for (uint32_t mask : {0x7Fu, 0x5Fu}) {
+        bool u[128] = {false};
+        for (uint32_t b = 0; b < 128; ++b)
+          if (used[b]) u[b & mask] = true;
+        uint32_t first = 128, last = 0;
+        for (uint32_t t = 0; t < 128; ++t)
+          if (u[t]) {
+            first = std::min(first, t);
+            last = t;
+          }
+        if (first > last) continue;
+        // widest gap inside [first, last] splits the cover in two
+        uint32_t gap_lo = 0, gap_len = 0, run_start = first;
+        for (uint32_t t = first; t <= last; ++t)
+          if (u[t]) {
+            if (t > run_start && t - run_start > gap_len) {
+              gap_len = t - run_start;
+              gap_lo = run_start;
+            }
+            run_start = t + 1;
+          }
+        ByteClass c;
+        c.run = run;
+        c.and_mask = mask;
+        if (gap_len) {
+          c.n_ranges = 2;
+          c.lo[0] = first;
+          c.hi[0] = gap_lo - 1;
+          c.lo[1] = gap_lo + gap_len;
+          c.hi[1] = last;
+        } else {
+          c.n_ranges = 1;
+          c.lo[0] = first;
+          c.hi[0] = last;
+        }
+        // cost = byte values (0..255) the class lets through
+        uint32_t cost = 0;
+        for (uint32_t b = 0; b < 256; ++b) cost += class_has(c, b);
+        cost = cost * 4 + c.n_ranges; // fewer values first, then fewer ranges
+        if (cost < best_cost) {
+          best_cost = cost;
+          best = c;
+        }
+      }
+      // worth its instructions only when it lets through a minority of the byte values
+      if (best.run && best_cost / 4 <= 96) d.cls = best;
+    }
+  }
+
   d.n_long = uint32_t(n_long);
   d.smallest = h.smallest;
   d.largest = h.largest;
@@ -271,12 +354,17 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
       const uint32_t b = g4_bit(d, gram);
       if (!(s.g4[b >> 5] >> (b & 31) & 1)) return nullptr;
     }
-    for (uint32_t b = slot_home(d, gram);; b = (b + 1) & d.slot_mask) {
-      const Slot &x = s.slots[2 * size_t(b)], &y = s.slots[2 * size_t(b) + 1];
-      if (x.meta != 0 && x.key == gram) return &x;
-      if (y.meta != 0 && y.key == gram) return &y;
-      if (x.meta == 0 || y.meta == 0) return nullptr;
+    for (uint32_t b = key_home(d, gram);; b = (b + 1) & d.key_mask) {
+      const uint32_t *k = reinterpret_cast<const uint32_t *>(&s.keys[b]);
+      for (uint32_t j = 0; j < 4; ++j)
+        if (k[j] == gram) return gram == d.empty_key ? nullptr : &s.slots[4 * size_t(b) + j];
+      if (k[3] == d.empty_key) return nullptr;
     }
+  };
+  auto in_class = [&](const uint8_t *p) {
+    for (uint32_t i = 0; i < d.cls.run; ++i)
+      if (!class_has(d.cls, p[i])) return false;
+    return true;
   };
   for (uint64_t p = 0; p < v.hdr.blob_bytes;) {
     const uint32_t gram = rd32(v.blob + p), count = rd32(v.blob + p + 4);
@@ -300,15 +388,17 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
       if (ok) {
         uint32_t w = 0;
         for (uint32_t i = 0; i < std::min<uint32_t>(pl - 4, 4); ++i) w |= uint32_t(v.patterns[po + 4 + i]) << (8 * i);
-        ok = w == got && std::memcmp(s.store.data() + po, v.patterns + po, pl) == 0;
+        ok = w == got && std::memcmp(s.store.data() + po, v.patterns + po, pl) == 0 && in_class(v.patterns + po);
       }
       bad += !ok;
     }
     p += 8 + 16ull * count;
   }
   for (uint32_t i = 0; i < v.n4; ++i) {
-    const Slot *sl = probe(rd32(v.arr4 + 4ull * i));
-    bad += !(sl && (sl->meta & kSlotShort4));
+    const uint32_t g4v = rd32(v.arr4 + 4ull * i);
+    const Slot *sl = probe(g4v);
+    const uint8_t g4b[4] = {uint8_t(g4v >> 24), uint8_t(g4v >> 16), uint8_t(g4v >> 8), uint8_t(g4v)};
+    bad += !(sl && (sl->meta & kSlotShort4) && (d.cls.run == 0 || (d.cls.run == 4 && in_class(g4b))));
   }
   auto p23_ok = [&](uint32_t gram) {
     const uint32_t b = p23_bit(d, gram);

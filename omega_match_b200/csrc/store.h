@@ -30,7 +30,8 @@ std::string parse_store(const uint8_t *file, size_t size, StoreView *out);
 
 // Host-side image of the device tables (device_tables.h), ready to be uploaded verbatim.
 struct StagedStore {
-  std::vector<Slot> slots;
+  std::vector<uint4> keys;  // buckets of four grams
+  std::vector<Slot> slots;  // 4 per bucket
   std::vector<Rec> recs;
   std::vector<uint8_t> store;
   std::vector<uint32_t> g4, p23, set3, bitmap2;
@@ -52,10 +53,18 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
 uint64_t check_staged_store(const StoreView &v, const StagedStore &s);
 
 // host mirror of the device hashing (scan.cu uses the same expressions)
-inline uint32_t slot_home(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.slot_shift; }
+inline uint32_t key_home(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.key_shift; }
 inline uint32_t g4_bit(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.g4_shift; }
 inline uint32_t p23_bit(const DeviceStore &d, uint32_t gram) {
   return ((gram & d.p23_and) * d.p23_mul) >> d.p23_shift;
+}
+// byte-class prefilter as the kernel evaluates it (device_tables.h ByteClass)
+inline bool class_has(const ByteClass &c, uint32_t b) {
+  if (b >= 0x80) return false;
+  const uint32_t t = b & c.and_mask;
+  for (uint32_t i = 0; i < c.n_ranges; ++i)
+    if (t >= c.lo[i] && t <= c.hi[i]) return true;
+  return false;
 }
 inline uint32_t set3_home(const DeviceStore &d, uint32_t key3) { return (key3 * kHashMul >> 8) & d.set3_mask; }
 
