@@ -82,10 +82,10 @@ struct EngineImpl {
   cudaStream_t stream = nullptr;
   Header hdr;
   DeviceStore ds;
-  uint32_t stages = 0, stage_cap = 0;
+  ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, tile_state, redo, misc, norm, map, windows, ghost, fscratch;
+  DevBuf hay, out, out2, tile_desc, tile_out, temp, redo, misc, norm, map, windows, ghost, fscratch;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -144,8 +144,8 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
   ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
-  impl->stages = scan_pick_stages(impl->ds, impl->smem_limit, &impl->stage_cap);
-  if (!ok || impl->stages == 0) {
+  impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit);
+  if (!ok || impl->geo.stages == 0) {
     delete eng;
     return fail("CUDA setup failed while uploading the store");
   }
@@ -163,7 +163,7 @@ Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
-                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->tile_state, &impl_->redo, &impl_->misc,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->tile_desc, &impl_->tile_out, &impl_->temp, &impl_->redo, &impl_->misc,
                     &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch})
     b->release();
   for (auto &ev : impl_->ev)
@@ -208,7 +208,6 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     std::fprintf(stderr, "libomega_match(b200): haystack too large for one call\n");
     return -1;
   }
-  if (E.tile_state.ensure((tiles + 1) * 8)) return -1;
   // misc: [0..kMaxBatches) u32 tickets | [..2*kMaxBatches) u32 redo counts | total (u64),
   // filter total (u64), counters[8]
   const size_t misc_total_off = size_t(kMaxBatches) * 8;
@@ -217,9 +216,12 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   unsigned int *d_redo_counts = d_tickets + kMaxBatches;
   const uint64_t tiles_per_launch = windowed ? uint64_t(kBatchWindows) * kTilesPerWindow : tiles;
   if (E.redo.ensure((tiles_per_launch + 1) * 4)) return -1;
+  if (E.tile_desc.ensure((tiles_per_launch + 1) * sizeof(TileDesc))) return -1;
+  if (E.tile_out.ensure((tiles_per_launch + 1) * 8)) return -1;
   unsigned long long *d_total = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + misc_total_off);
   unsigned long long *d_ftotal = d_total + 1;
   unsigned long long *d_counters = d_total + 2;
+  unsigned long long *d_temp_count = d_total + 10;
 
   const bool identity_map = windowed && !(E.hdr.flags & (kFlagIgnorePunct | kFlagElideSpace));
   if (windowed) {
@@ -246,7 +248,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   for (int attempt = 0; attempt < 3; ++attempt) {
     if (E.out.ensure(cap * sizeof(Record))) return -1;
     cap = E.out.cap / sizeof(Record);
-    OLM_CUDA(cudaMemsetAsync(E.tile_state.p, 0, (tiles + 1) * 8, E.stream));
+    if (E.temp.ensure(cap * 4)) return -1;
     OLM_CUDA(cudaMemsetAsync(d_tickets, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_redo_counts, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_total, 0, 128, E.stream));
@@ -255,15 +257,20 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
 
     ScanParams P{};
     P.st = E.ds;
-    P.tile_state = static_cast<unsigned long long *>(E.tile_state.p);
+    P.tile_desc = static_cast<TileDesc *>(E.tile_desc.p);
+    P.out_base = static_cast<unsigned long long *>(E.tile_out.p);
+    P.temp = static_cast<uint32_t *>(E.temp.p);
+    P.temp_cap = cap;
+    P.temp_count = d_temp_count;
     P.out = static_cast<Record *>(E.out.p);
     P.out_cap = cap;
     P.match_ptr_base = r.match_ptr_base;
     P.total = d_total;
     P.counters = d_counters;
     P.flags = fl;
-    P.stages = E.stages;
-    P.stage_cap = E.stage_cap;
+    P.stages = E.geo.stages;
+    P.sets = E.geo.sets;
+    P.chunk_cap = E.geo.chunk_cap;
     P.tail_byte = 0;
     P.redo_list = static_cast<uint32_t *>(E.redo.p);
 
@@ -275,7 +282,6 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
       P.scan_begin = r.own_begin;
       P.scan_end = r.own_end;
       P.num_tiles = (uint32_t)tiles;
-      P.tile_base = 0;
       P.ticket = d_tickets;
       P.redo_count = d_redo_counts;
       OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
@@ -308,7 +314,6 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.win_src_base = r.own_begin + w0 * kWindowBytes;
         P.tiles_per_win = kTilesPerWindow;
         P.num_tiles = nw * kTilesPerWindow;
-        P.tile_base = (uint32_t)(w0 * kTilesPerWindow);
         P.ticket = d_tickets + b;
         P.redo_count = d_redo_counts + b;
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));

@@ -7,32 +7,39 @@
 // concatenate + radix sort of finalize_match_results (matcher.c:587-623, :258-325).
 //
 // Shape of scan_kernel
-//   * persistent CTAs (grid = #SMs): 16 scanning warps + 1 control warp.  Tiles of 16 KiB
-//     positions are handed out by an atomic ticket, so tile k is always started before k+1;
-//   * control warp, producer half: each tile (+16 bytes in front, +112 behind) is brought into
-//     shared memory by ONE cp.async.bulk (TMA, 1-D) that completes on a `full` mbarrier; a ring
-//     of up to 4 stages keeps ~64 KiB per SM in flight; a stage is refilled as soon as all 16
-//     scanning warps have arrived on its `scanned` mbarrier -- no CTA-wide barrier anywhere;
+//   * persistent CTAs (grid = #SMs) of 32 warps: 30 scanning warps, one finisher warp, one
+//     producer warp.  Tiles of 16 KiB positions are handed out by an atomic ticket, so tile k
+//     is always started before k+1; inside a CTA the 32 chunks (512 positions) of a tile are
+//     grabbed dynamically by the scanning warps -- no warp waits for a slower one;
+//   * producer: each tile (+16 bytes in front, +112 behind) is brought into shared memory by
+//     ONE cp.async.bulk (TMA, 1-D, L2 evict-first) that completes on a `full` mbarrier; ring of
+//     2..4 stages; a stage is refilled as soon as its 32 chunks have arrived on `scanned` --
+//     no CTA-wide barrier anywhere;
 //   * stage 1, every position, in registers:
 //       - stores whose patterns all start with a run of bytes from a small class (letters ...):
 //         SWAR range tests on the haystack words -> 1 bit per position (no memory access);
 //       - else: big-endian gram by PRMT from two registers, one multiply, one probe of the
 //         hashed gram bitmap in shared memory (and one of the short-pattern bitmap when the
 //         store has 1..3 byte patterns);
-//     survivors are compacted, in position order, into the warp's queue;
-//   * stage 2, queue entries, 32 x kProbeUnroll at a time: position predicates, (class mode:
-//     the gram bitmap probe,) ONE 16-byte load of the gram's key bucket -- almost every false
-//     candidate ends here --, on a key hit the slot (pattern bytes 4..11 + length), remaining
-//     bytes against the pattern store, end predicates, then the 4/3/2/1-byte sets;
-//   * emission: accepted matches are appended in candidate order (ballot + popc) to the warp's
-//     staging area of the tile (two areas per warp, tiles alternate);
-//   * control warp, look-back half: warp totals of tile k -> exclusive prefixes, a decoupled
-//     look-back over the tile descriptors yields the tile's global base; the scanning warps
-//     copy tile k's staged matches to their FINAL place in the result array (offset
-//     ascending, length descending: no sort pass) after they have scanned tile k+1;
+//     survivors are compacted, in position order, into the warp's queue Q1;
+//   * stage 2a, Q1 entries, 32 x kProbeUnroll at a time: position predicates, (class mode: the
+//     gram bitmap probe,) ONE 16-byte load of the gram's key bucket -- almost every false
+//     candidate ends here; key hits (and short-pattern candidates) are compacted into Q2;
+//   * stage 2b, Q2 entries, 32 at a time, all lanes busy: the slot (pattern bytes 4..11 +
+//     length), remaining bytes against the pattern store, end predicates, the 4/3/2/1-byte
+//     sets; accepted matches are appended in candidate order (ballot + popc) to the chunk's
+//     staging area;
+//   * finisher: chunk totals of tile k -> exclusive prefixes (one chunk per lane), ONE global
+//     atomic reserves the tile's run in temp[], the staged matches go there as packed 4-byte
+//     entries (position order) and the tile descriptor {count, temp_base} is written.  No CTA
+//     ever waits for another CTA.  Staging sets rotate, so scanning runs ahead of the finisher;
+//   * prefix_kernel: exclusive prefix over the tile counts = every tile's first index in the
+//     result array;  place_kernel: expands the packed entries into final 24-byte records at
+//     those indices (offset ascending, length descending: the order radix_sort_matches
+//     produces, without a sort);
 //   * a tile whose matches do not fit the staging area goes on the redo list; redo_kernel
-//     (launched right after, exits at once when the list is empty) re-evaluates such tiles
-//     and writes to HBM directly (counts are always exact, so bases do not change).
+//     (exits at once when the list is empty) re-evaluates such tiles and writes their records
+//     directly (counts are always exact, so bases do not change).
 #include "scan.cuh"
 
 #include <cstdio>
@@ -44,9 +51,6 @@ namespace olm {
 
 namespace {
 
-constexpr unsigned long long kStateAggregate = 1ull << 62;
-constexpr unsigned long long kStatePrefix = 2ull << 62;
-constexpr unsigned long long kStateValueMask = (1ull << 62) - 1;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 
@@ -60,27 +64,20 @@ struct StageInfo { // written by the producer lane, read by everyone after the m
   uint32_t tail;
   uint32_t win;
   uint32_t staged;         // bytes valid behind p0 in the stage buffer
-  uint32_t _pad[2];
+  uint32_t seq;            // tile iteration of the CTA this entry describes (written first)
+  uint32_t _pad;
 };
 static_assert(sizeof(StageInfo) == 64, "StageInfo is 64 bytes");
-
-struct TileOut { // what the copy-out of a tile needs after its stage has been refilled
-  unsigned long long p0, emit_base;
-  uint32_t win, _pad;
-};
 
 // shared memory header (kSmemHeader bytes)
 struct SmemHeader {
   uint64_t full[kMaxStages];
   uint64_t scanned[kMaxStages];
-  uint64_t ready[2];
-  uint32_t ovf[2];       // set by scanning warps while they stage a tile
-  uint32_t ovf_final[2]; // what the copy-out looks at
-  unsigned long long base[2];
-  uint32_t wcnt[2][kScanWarps];
-  uint32_t wpre[2][kScanWarps];
-  TileOut tout[2];
-  StageInfo info[kMaxStages];
+  uint32_t chunk_ctr; // next chunk of the CTA's tile sequence
+  uint32_t drained;   // tiles whose staged matches have been copied out (finisher)
+  uint32_t ovf[kMaxSets];
+  uint32_t ccnt[kMaxSets][kTileChunks];
+  StageInfo info[kInfoRing];
 };
 static_assert(sizeof(SmemHeader) <= kSmemHeader, "header does not fit");
 
@@ -115,24 +112,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 // 1-D bulk copy global -> shared through the TMA unit; completes `bytes` on `bar`.
+// The haystack is read once: L2 evict-first keeps the tables resident instead.
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
-// Tile descriptors carry their whole payload in one 64-bit word, so relaxed accesses are
-// enough (nothing else written by the other CTA is read) -- and, unlike acquire loads, they do
-// not make ptxas invalidate L1 (CCTL.IVALL) on every poll.
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // little-endian 32-bit word at an arbitrary shared-memory byte address
 __device__ __forceinline__ uint32_t lds_le32(const uint8_t *q) {
   const uint32_t a = smem_u32(q);
@@ -151,6 +140,22 @@ struct TileCtx {
   uint32_t staged, tail;
   bool first;      // p0 == 0
 };
+
+// One final record.  `pos` is segment relative; with a map (window mode) it is translated back
+// to source coordinates (matcher.c:986-997).
+__device__ __forceinline__ void put_record(const ScanParams &P, unsigned long long r, unsigned long long emit_base,
+                                           unsigned long long pos, uint32_t len, const uint32_t *map) {
+  unsigned long long off = emit_base + pos;
+  if (map) {
+    const uint32_t a = __ldg(map + pos), b = __ldg(map + pos + len - 1);
+    off = emit_base + a;
+    len = b - a + 1;
+  }
+  Record *o = P.out + r;
+  o->offset = off;
+  *reinterpret_cast<unsigned long long *>(&o->len) = (unsigned long long)len;
+  o->ptr = P.match_ptr_base + off;
+}
 
 enum ChunkMode { kStageMode = 0, kCountMode = 1, kDirectMode = 2 };
 
@@ -225,11 +230,14 @@ struct Scanner {
     return true;
   }
 
-  // ---- one candidate position, split in two so that several probes can be in flight ----
+  // ---- one candidate position in three steps, so that many loads are in flight ----
   // probe_issue : position predicates (matcher.c:770-776, :195-196, :806-807), the gram,
   //               (class mode: the gram bitmap,) and the load of the gram's key bucket;
-  // probe_finish: everything else the reference does for the position (matcher.c:782-880);
+  // probe_key   : the key compare; yields the slot index of a hit (or kNoSlot) and whether
+  //               the position goes on to
+  // verify      : everything else the reference does for the position (matcher.c:782-880);
   //               `emit(len)` is called once per accepted match, longest first.
+  static constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
   struct Probe {
     uint32_t tpos, gram, bucket, flags; // flags: 1 = alive, 2 = gram candidate (and >= 4 bytes left), 4 = short candidate
     uint4 kb;
@@ -260,7 +268,7 @@ struct Scanner {
     pr.flags = 1u | (cand_p ? 4u : 0u);
     if (HAS_G4 && cand_g && T.rem0 - tpos >= 4) {
       const uint32_t h = gram * kHashMul;
-      if (HAS_CLS) { // the queue holds class survivors: the gram bitmap is probed here
+      if (HAS_CLS) { // Q1 holds class survivors: the gram bitmap is probed here
         const uint32_t b = h >> P.st.g4_shift;
         if (!((g4s[b >> 5] >> (b & 31)) & 1u)) return;
       }
@@ -270,80 +278,88 @@ struct Scanner {
     }
   }
 
-  template <typename Emit>
-  __device__ __forceinline__ void probe_finish(const TileCtx &T, const Probe &pr, Emit &&emit) const {
-    if (!(pr.flags & 1u)) return;
-    const uint32_t tpos = pr.tpos, gram = pr.gram;
-    const uint32_t rem = T.rem0 - tpos;
-    const uint8_t *q = T.sb + kTilePre + tpos;
-    bool emitted = false;
-    const bool longest = fl & kLongestOnly;
-
+  // returns true when the position needs verify(); *slot = slot index of the gram or kNoSlot
+  __device__ __forceinline__ bool probe_key(const Probe &pr, uint32_t *slot) const {
+    *slot = kNoSlot;
+    if (!(pr.flags & 1u)) return false;
     if (HAS_G4 && (pr.flags & 2u)) {
       // the gram is in the first bucket (from its home) that has it; a bucket whose last
       // place is unused ends the probe
+      const uint32_t gram = pr.gram;
       uint4 kb = pr.kb;
       uint32_t bucket = pr.bucket;
-      int place = -1;
+      int place;
       while (true) {
         place = kb.x == gram ? 0 : kb.y == gram ? 1 : kb.z == gram ? 2 : kb.w == gram ? 3 : -1;
         if (place >= 0 || kb.w == P.st.empty_key) break;
         bucket = (bucket + 1) & P.st.key_mask;
         kb = __ldg(P.st.keys + bucket);
       }
-      if (place >= 0) {
-        const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + (4 * (size_t)bucket + place)));
-        const uint32_t meta = s.z; // 0 when the gram equals empty_key and matched an unused place
-        if (meta != 0) {
-          const uint32_t hay4 = lds_le32(q + 4), hay8 = lds_le32(q + 8);
-          if (meta & kSlotValueMask) {
-            n_hits += stat_inc;
-            n_long_hits += stat_inc;
+      if (place >= 0) *slot = 4 * bucket + (uint32_t)place;
+    }
+    return *slot != kNoSlot || (HAS_P23 && (pr.flags & 4u));
+  }
+
+  template <typename Emit>
+  __device__ __forceinline__ void verify(const TileCtx &T, uint32_t tpos, uint32_t slot, bool cand_p, Emit &&emit) const {
+    const uint32_t rem = T.rem0 - tpos;
+    const uint8_t *q = T.sb + kTilePre + tpos;
+    bool emitted = false;
+    const bool longest = fl & kLongestOnly;
+
+    if (HAS_G4 && slot != kNoSlot) {
+      const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + slot));
+      const uint32_t meta = s.z; // 0 when the gram equals empty_key and matched an unused place
+      if (meta != 0) {
+        const uint32_t hay4 = lds_le32(q + 4), hay8 = lds_le32(q + 8);
+        if (meta & kSlotValueMask) {
+          n_hits += stat_inc;
+          n_long_hits += stat_inc;
+        }
+        // bytes 4..11 of a pattern of length len against the haystack
+        auto head_equal = [&](uint32_t len, uint32_t n4, uint32_t n8) {
+          const uint32_t m4 = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
+          const uint32_t m8 = len >= 12 ? kFull : (len > 8 ? ((1u << ((len - 8) * 8)) - 1u) : 0u);
+          return (((hay4 ^ n4) & m4) | ((hay8 ^ n8) & m8)) == 0;
+        };
+        if (meta & kSlotMulti) {
+          const uint32_t cnt = meta & kSlotValueMask;
+          for (uint32_t j = 0; j < cnt; ++j) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
+            const uint32_t len = r.y;
+            if (len > rem) continue; // matcher.c:203
+            n_cmp += stat_inc;
+            if (!head_equal(len, r.x, r.w)) continue;
+            if (len > 12 && !tail_equal(T, tpos, len, r.z)) continue;
+            if (!end_ok_long(T, tpos, len)) continue;
+            emit(len);
+            emitted = true;
+            if (longest) break;
           }
-          // bytes 4..11 of a pattern of length len against the haystack
-          auto head_equal = [&](uint32_t len, uint32_t n4, uint32_t n8) {
-            const uint32_t m4 = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
-            const uint32_t m8 = len >= 12 ? kFull : (len > 8 ? ((1u << ((len - 8) * 8)) - 1u) : 0u);
-            return (((hay4 ^ n4) & m4) | ((hay8 ^ n8) & m8)) == 0;
-          };
-          if (meta & kSlotMulti) {
-            const uint32_t cnt = meta & kSlotValueMask;
-            for (uint32_t j = 0; j < cnt; ++j) {
-              const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
-              const uint32_t len = r.y;
-              if (len > rem) continue; // matcher.c:203
-              n_cmp += stat_inc;
-              if (!head_equal(len, r.x, r.w)) continue;
-              if (len > 12 && !tail_equal(T, tpos, len, r.z)) continue;
-              if (!end_ok_long(T, tpos, len)) continue;
+        } else {
+          const uint32_t len = meta & kSlotValueMask;
+          if (len != 0 && len <= rem) {
+            n_cmp += stat_inc;
+            if (head_equal(len, s.x, s.y) && (len <= 12 || tail_equal(T, tpos, len, s.w)) &&
+                end_ok_long(T, tpos, len)) {
               emit(len);
               emitted = true;
-              if (longest) break;
-            }
-          } else {
-            const uint32_t len = meta & kSlotValueMask;
-            if (len != 0 && len <= rem) {
-              n_cmp += stat_inc;
-              if (head_equal(len, s.x, s.y) && (len <= 12 || tail_equal(T, tpos, len, s.w)) &&
-                  end_ok_long(T, tpos, len)) {
-                emit(len);
-                emitted = true;
-              }
             }
           }
-          if ((meta & kSlotShort4) && !(longest && emitted)) {
-            if (end_ok_short(T, tpos, 4)) {
-              emit(4u);
-              emitted = true;
-              n_hits += stat_inc;
-            } else {
-              n_miss += stat_inc;
-            }
+        }
+        if ((meta & kSlotShort4) && !(longest && emitted)) {
+          if (end_ok_short(T, tpos, 4)) {
+            emit(4u);
+            emitted = true;
+            n_hits += stat_inc;
+          } else {
+            n_miss += stat_inc;
           }
         }
       }
     }
-    if (HAS_P23 && (pr.flags & 4u) && !(longest && emitted)) {
+    if (HAS_P23 && cand_p && !(longest && emitted)) {
+      const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
       if (P.st.n3 && rem >= 3) {
         const uint32_t k3 = gram >> 8;
         bool hit = false;
@@ -439,20 +455,88 @@ struct Scanner {
     }
   }
 
-  // One 512-byte chunk of a warp.  The warp's candidates are compacted into a queue in
-  // position order; then every lane takes one candidate per sub-step, kProbeUnroll sub-steps
-  // are issued together (their bucket loads overlap), and accepted matches are appended in
-  // candidate order (ballot + popc; a shuffle scan only when a position has several matches;
-  // a position with more than four matches is evaluated a second time for the rest).
+  // Stage 2b for up to 32 entries of Q2 (lane i takes entry i): verify, then append the
+  // accepted matches in entry order (ballot + popc; a shuffle scan only when a position has
+  // several matches; a position with more than four matches is evaluated a second time for
+  // the rest).  Returns the number of matches of the batch.
   //   kStageMode : matches go to `stage` (packed, shared memory, `cap` entries); when they
   //                do not fit, *overflow is set (the tile goes on the redo list);
   //   kCountMode : nothing is written;
   //   kDirectMode: matches go to P.out[out_base ...] as final records.
-  // Returns the exact number of matches of the chunk in all modes.
-  static constexpr int kProbeUnroll = 4;
+  template <int MODE>
+  __device__ __forceinline__ uint32_t verify_batch(const TileCtx &T, const unsigned long long *q2, uint32_t n,
+                                                   uint32_t lane, uint32_t *stage, uint32_t used, uint32_t cap,
+                                                   unsigned long long out_base, unsigned long long emit_base,
+                                                   const uint32_t *map, uint32_t *overflow) const {
+    const bool mine = lane < n;
+    const unsigned long long ent = mine ? q2[lane] : 0ull;
+    const uint32_t slot = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
+    const uint32_t tpos = hi & 0xFFFFu;
+    const bool cand_p = (hi >> 16) & 1u;
+    uint32_t cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (mine)
+      verify(T, tpos, slot, cand_p, [&](uint32_t len) {
+        if (cnt == 0) m0 = len;
+        else if (cnt == 1) m1 = len;
+        else if (cnt == 2) m2 = len;
+        else if (cnt == 3) m3 = len;
+        ++cnt;
+      });
+    const uint32_t bal = __ballot_sync(kFull, cnt > 0);
+    if (!bal) return 0;
+    uint32_t pre, tot;
+    const bool many = __any_sync(kFull, cnt > 1);
+    if (!many) {
+      pre = __popc(bal & ((1u << lane) - 1u));
+      tot = __popc(bal);
+    } else {
+      uint32_t in2 = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, in2, d);
+        if (lane >= (uint32_t)d) in2 += t;
+      }
+      pre = in2 - cnt;
+      tot = __shfl_sync(kFull, in2, 31);
+    }
+    const uint32_t at = used + pre;
+    auto put = [&](uint32_t i, uint32_t len) {
+      if (MODE == kDirectMode) {
+        const unsigned long long r = out_base + at + i;
+        if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
+      } else if (MODE == kStageMode) {
+        if (at + i < cap && !(len >> kPackLenBits)) {
+          stage[at + i] = (tpos << kPackLenBits) | len;
+        } else {
+          *overflow = 1;
+        }
+      }
+    };
+    if (cnt > 0) put(0, m0);
+    if (cnt > 1) put(1, m1);
+    if (cnt > 2) put(2, m2);
+    if (cnt > 3) put(3, m3);
+    if (MODE != kCountMode && many && __any_sync(kFull, cnt > 4)) {
+      if (cnt > 4) { // evaluate the position again for matches 5, 6, ...
+        uint32_t i = 0;
+        const uint32_t keep = stat_inc;
+        stat_inc = 0;
+        verify(T, tpos, slot, cand_p, [&](uint32_t len) {
+          if (i >= 4) put(i, len);
+          ++i;
+        });
+        stat_inc = keep;
+      }
+    }
+    return tot;
+  }
+
+  // One 512-byte chunk: stage 1 -> Q1 -> key probes (kProbeUnroll x 32 in flight) -> Q2 ->
+  // verify batches.  Returns the exact number of matches of the chunk in all modes.
+  static constexpr int kProbeUnroll = 2;
   template <int MODE>
   __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t *stage,
-                                                 uint32_t used, uint32_t cap, uint16_t *queue,
+                                                 uint32_t cap, uint16_t *q1, unsigned long long *q2,
                                                  unsigned long long out_base, unsigned long long emit_base,
                                                  const uint32_t *map, uint32_t *overflow) const {
     uint32_t cg, cp;
@@ -474,11 +558,11 @@ struct Scanner {
       while (cand) {
         const uint32_t k = __ffs(cand) - 1;
         cand &= cand - 1;
-        queue[o++] = (uint16_t)((lane * 16 + k) | (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10));
+        q1[o++] = (uint16_t)((lane * 16 + k) | (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10));
       }
     }
     __syncwarp();
-    uint32_t found = 0;
+    uint32_t found = 0, q2n = 0;
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t base = 0; base < total; base += 32 * kProbeUnroll) {
       Probe pr[kProbeUnroll];
@@ -486,85 +570,40 @@ struct Scanner {
       for (int u = 0; u < kProbeUnroll; ++u) {
         const uint32_t idx = base + u * 32 + lane;
         const bool ok = idx < total;
-        const uint32_t e = ok ? queue[idx] : 0u;
+        const uint32_t e = ok ? q1[idx] : 0u;
         probe_issue(T, ok, cbase + (e & 511u), (e >> 9) & 1u, (e >> 10) & 1u, pr[u]);
       }
 #pragma unroll
       for (int u = 0; u < kProbeUnroll; ++u) {
         if (base + u * 32 >= total) break;
-        uint32_t n = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        const uint32_t tpos = pr[u].tpos;
-        probe_finish(T, pr[u], [&](uint32_t len) {
-          if (n == 0) m0 = len;
-          else if (n == 1) m1 = len;
-          else if (n == 2) m2 = len;
-          else if (n == 3) m3 = len;
-          ++n;
-        });
-        const uint32_t bal = __ballot_sync(kFull, n > 0);
+        uint32_t slot;
+        const bool want = probe_key(pr[u], &slot);
+        const uint32_t bal = __ballot_sync(kFull, want);
         if (!bal) continue;
-        uint32_t pre, tot;
-        const bool many = __any_sync(kFull, n > 1);
-        if (!many) {
-          pre = __popc(bal & lt);
-          tot = __popc(bal);
-        } else {
-          uint32_t in2 = n;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, in2, d);
-            if (lane >= (uint32_t)d) in2 += t;
-          }
-          pre = in2 - n;
-          tot = __shfl_sync(kFull, in2, 31);
+        if (want)
+          q2[q2n + __popc(bal & lt)] =
+              ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 4u) << 14)) << 32) | slot;
+        q2n += __popc(bal);
+        __syncwarp();
+        if (q2n >= 32) {
+          found += verify_batch<MODE>(T, q2, 32, lane, stage, found, cap, out_base, emit_base, map, overflow);
+          const uint32_t rest = q2n - 32;
+          const unsigned long long mv = lane < rest ? q2[32 + lane] : 0ull;
+          __syncwarp();
+          if (lane < rest) q2[lane] = mv;
+          __syncwarp();
+          q2n = rest;
         }
-        const uint32_t at = used + found + pre;
-        auto put = [&](uint32_t i, uint32_t len) {
-          if (MODE == kDirectMode) {
-            const unsigned long long r = out_base + at + i;
-            if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
-          } else if (MODE == kStageMode) {
-            if (at + i < cap && !(len >> kPackLenBits)) {
-              stage[at + i] = (tpos << kPackLenBits) | len;
-            } else {
-              *overflow = 1;
-            }
-          }
-        };
-        if (n > 0) put(0, m0);
-        if (n > 1) put(1, m1);
-        if (n > 2) put(2, m2);
-        if (n > 3) put(3, m3);
-        if (MODE != kCountMode && many && __any_sync(kFull, n > 4)) {
-          if (n > 4) { // evaluate the position again for matches 5, 6, ...
-            uint32_t i = 0;
-            stat_inc = 0;
-            probe_finish(T, pr[u], [&](uint32_t len) {
-              if (i >= 4) put(i, len);
-              ++i;
-            });
-            stat_inc = 1;
-          }
-        }
-        found += tot;
       }
     }
+    if (q2n) found += verify_batch<MODE>(T, q2, q2n, lane, stage, found, cap, out_base, emit_base, map, overflow);
     __syncwarp();
     return found;
   }
 
   __device__ __forceinline__ void write_record(unsigned long long r, unsigned long long emit_base,
                                                unsigned long long pos, uint32_t len, const uint32_t *map) const {
-    unsigned long long off = emit_base + pos;
-    if (map) { // matcher.c:986-997: back to source coordinates
-      const uint32_t a = __ldg(map + pos), b = __ldg(map + pos + len - 1);
-      off = emit_base + a;
-      len = b - a + 1;
-    }
-    Record *o = P.out + r;
-    o->offset = off;
-    *reinterpret_cast<unsigned long long *>(&o->len) = (unsigned long long)len;
-    o->ptr = P.match_ptr_base + off;
+    put_record(P, r, emit_base, pos, len, map);
   }
 
   __device__ __forceinline__ void flush_stats(uint32_t lane) const {
@@ -585,8 +624,8 @@ struct Scanner {
   }
 };
 
-// Fills `I` for launch-local tile t and starts its bulk copy into `dst` (a stage buffer).
-__device__ __forceinline__ void start_tile(const ScanParams &P, uint32_t t, StageInfo &I, uint8_t *dst, uint64_t *bar) {
+// Fills `I` for launch-local tile t ...
+__device__ __forceinline__ void fill_tile(const ScanParams &P, uint32_t t, StageInfo &I) {
   I.tile = t;
   uint32_t win = 0;
   if (P.flags & kWindowMode) {
@@ -609,16 +648,25 @@ __device__ __forceinline__ void start_tile(const ScanParams &P, uint32_t t, Stag
   I.win = win;
   I.staged = 0;
   if (I.p0 < I.end) {
-    const long long pre = I.boff >= kTilePre ? kTilePre : 0;
     long long e = I.boff + kTileBytes + kTileHalo;
     if (e > (long long)P.buf_len) e = (long long)P.buf_len;
-    const uint32_t bytes = (uint32_t)(e - (I.boff - pre));
     I.staged = (uint32_t)(e - I.boff);
+  }
+}
+// ... and starts its bulk copy into `dst` (a stage buffer), completing on `bar`.
+__device__ __forceinline__ void copy_tile(const ScanParams &P, const StageInfo &I, uint8_t *dst, uint64_t *bar) {
+  if (I.p0 < I.end) {
+    const long long pre = I.boff >= kTilePre ? kTilePre : 0;
+    const uint32_t bytes = (uint32_t)(I.staged + pre);
     mbar_expect_tx(bar, bytes);
     tma_load_1d(dst + (kTilePre - pre), P.buf + (I.boff - pre), bytes, bar);
   } else {
     mbar_expect_tx(bar, 0); // empty tile: the phase completes at once
   }
+}
+__device__ __forceinline__ void start_tile(const ScanParams &P, uint32_t t, StageInfo &I, uint8_t *dst, uint64_t *bar) {
+  fill_tile(P, t, I);
+  copy_tile(P, I, dst, bar);
 }
 
 __device__ __forceinline__ void tile_ctx(const StageInfo &I, const uint8_t *sb, TileCtx &T) {
@@ -638,8 +686,10 @@ struct SmemLayout {
   SmemHeader *H;
   uint8_t *ring;
   uint32_t *g4s, *p23s, *staging;
-  uint16_t *queues;
+  uint16_t *q1;
+  unsigned long long *q2;
 };
+// header | ring | g4 | p23 | Q2 (8-byte entries) | staging | Q1
 template <bool HAS_G4, bool HAS_P23>
 __device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, uint32_t stages, uint32_t staging_words) {
   SmemLayout L;
@@ -647,8 +697,9 @@ __device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, 
   L.ring = smem + kSmemHeader;
   L.g4s = reinterpret_cast<uint32_t *>(L.ring + (size_t)stages * kStageBytes);
   L.p23s = L.g4s + (HAS_G4 ? P.st.g4_words : 0);
-  L.staging = L.p23s + (HAS_P23 ? P.st.p23_words : 0);
-  L.queues = reinterpret_cast<uint16_t *>(L.staging + staging_words);
+  L.q2 = reinterpret_cast<unsigned long long *>(L.p23s + (HAS_P23 ? P.st.p23_words : 0));
+  L.staging = reinterpret_cast<uint32_t *>(L.q2 + kScanWarps * kQ2Entries);
+  L.q1 = reinterpret_cast<uint16_t *>(L.staging + staging_words);
   return L;
 }
 template <bool HAS_G4, bool HAS_P23>
@@ -665,12 +716,15 @@ __device__ __forceinline__ void load_filters(const SmemLayout &L, const ScanPara
   }
 }
 
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
+  return *reinterpret_cast<const volatile uint32_t *>(p);
+}
+
 template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t S = P.stages;
-  const uint32_t cap = P.stage_cap;
-  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, 2u * kScanWarps * cap);
+  const uint32_t S = P.stages, NB = P.sets, cap = P.chunk_cap;
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, NB * kTileChunks * cap);
   SmemHeader &H = *L.H;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -680,87 +734,109 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   if (tid == 0) {
     for (uint32_t s = 0; s < kMaxStages; ++s) {
       mbar_init(&H.full[s], 1);
-      mbar_init(&H.scanned[s], kScanWarps);
+      mbar_init(&H.scanned[s], kTileChunks);
     }
-    mbar_init(&H.ready[0], 1);
-    mbar_init(&H.ready[1], 1);
-    H.ovf[0] = H.ovf[1] = 0;
-    H.ovf_final[0] = H.ovf_final[1] = 0;
+    H.chunk_ctr = 0;
+    H.drained = 0;
+    for (uint32_t b = 0; b < kMaxSets; ++b) H.ovf[b] = 0;
+    for (uint32_t i = 0; i < kInfoRing; ++i) H.info[i].seq = kNoTile;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == kScanWarps) {
-    // ================= control warp: TMA producer + decoupled look-back =================
-    auto produce = [&](uint32_t s) { // lane 0 only
+  if (warp == kScanWarps + 1) {
+    // ============================ producer warp (one lane) ============================
+    if (lane != 0) return;
+    // Tile iteration k of this CTA -> stage k % S.  The info entry is published with a fence +
+    // volatile `seq` store: readers that do not wait on `full` (the finisher) spin on seq.
+    auto produce = [&](uint32_t k) {
+      const uint32_t s = k % S;
       const uint32_t t = atomicAdd(P.ticket, 1u);
-      StageInfo &I = H.info[s];
+      StageInfo &I = H.info[k % kInfoRing];
       if (t >= P.num_tiles) {
         I.tile = kNoTile;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t *>(&I.seq) = k;
         mbar_expect_tx(&H.full[s], 0);
         return;
       }
-      start_tile(P, t, I, L.ring + (size_t)s * kStageBytes, &H.full[s]);
+      fill_tile(P, t, I);
+      __threadfence_block();
+      *reinterpret_cast<volatile uint32_t *>(&I.seq) = k;
+      copy_tile(P, I, L.ring + (size_t)s * kStageBytes, &H.full[s]);
     };
-    if (lane == 0)
-      for (uint32_t s = 0; s < S; ++s) produce(s);
-    __syncwarp();
+    // tiles claimed ahead: the ring depth, but not more than this CTA's fair share (small inputs)
+    const uint32_t share = (P.num_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t D = share < S ? (share ? share : 1u) : S;
+    for (uint32_t k = 0; k < D; ++k) produce(k);
     uint32_t s = 0, ph = 0;
     for (uint32_t k = 0;; ++k) {
-      const uint32_t tile = *reinterpret_cast<const volatile uint32_t *>(&H.info[s].tile);
-      __syncwarp(); // every lane has read the stage info before lane 0 refills the stage
-      if (tile == kNoTile) break;
+      if (H.info[k % kInfoRing].tile == kNoTile) break;
       mbar_wait(&H.scanned[s], ph);
-      const uint32_t b = k & 1;
-      if (lane == 0) {
-        H.tout[b].p0 = H.info[s].p0;
-        H.tout[b].emit_base = H.info[s].emit_base;
-        H.tout[b].win = H.info[s].win;
-        produce(s); // the stage buffer is free again
+      produce(k + D); // stage (k + D) % S last held tile k + D - S <= k: free
+      if (++s == S) {
+        s = 0;
+        ph ^= 1;
       }
-      // warp totals -> exclusive prefixes; then the decoupled look-back for the tile base
-      uint32_t c = lane < kScanWarps ? H.wcnt[b][lane] : 0, incl = c;
+    }
+    return;
+  }
+
+  if (warp == kScanWarps) {
+    // ============ finisher warp: tile descriptor + staged matches -> temp[] ============
+    uint32_t s = 0, ph = 0;
+    for (uint32_t k = 0;; ++k) {
+      const StageInfo &I = H.info[k % kInfoRing];
+      // (no wait on `full` here: the finisher may lag the producer by more than one
+      // generation of the stage, and an mbarrier only tells two phases apart)
+      while (ld_volatile_shared(&I.seq) != k) __nanosleep(32);
+      __threadfence_block();
+      const uint32_t tile = I.tile;
+      if (tile == kNoTile) break;
+      // sets <= stages (scan_pick_geometry), so tile k + S cannot be scanned before tile k has
+      // been finished: this wait is never more than one generation behind
+      mbar_wait(&H.scanned[s], ph);
+      const uint32_t b = k % NB;
+      // chunk totals -> exclusive prefixes (lane = chunk)
+      const uint32_t c = H.ccnt[b][lane];
+      uint32_t incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(kFull, incl, d);
         if (lane >= (uint32_t)d) incl += t;
       }
-      if (lane < kScanWarps) H.wpre[b][lane] = incl - c;
-      const unsigned long long tile_total = __shfl_sync(kFull, incl, 31);
-      const long long g = (long long)P.tile_base + tile;
-      unsigned long long excl = 0;
-      if (g > 0) {
-        if (lane == 0) st_relaxed(P.tile_state + g, kStateAggregate | tile_total);
-        long long j = g - 1;
-        while (true) {
-          const long long mine = j - lane;
-          unsigned long long v = kStatePrefix; // virtual predecessor of tile 0: prefix 0
-          if (mine >= 0) {
-            do {
-              v = ld_relaxed(P.tile_state + mine);
-            } while ((v >> 62) == 0);
-          }
-          const uint32_t is_prefix = __ballot_sync(kFull, (v >> 62) == 2);
-          const uint32_t first = is_prefix ? (__ffs(is_prefix) - 1) : 32;
-          unsigned long long add = lane <= first ? (v & kStateValueMask) : 0;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) add += __shfl_xor_sync(kFull, add, d);
-          excl += add;
-          if (is_prefix) break;
-          j -= 32;
-        }
-      }
+      const uint32_t cpre = incl - c;
+      const uint32_t tile_total = __shfl_sync(kFull, incl, 31);
+      const uint32_t ovf = H.ovf[b];
+      unsigned long long base = 0;
       if (lane == 0) {
-        st_relaxed(P.tile_state + g, kStatePrefix | (excl + tile_total));
-        H.base[b] = excl;
-        if (tile == P.num_tiles - 1) *P.total = excl + tile_total;
-        const uint32_t ovf = H.ovf[b];
-        H.ovf_final[b] = ovf;
-        H.ovf[b] = 0;
+        if (tile_total && !ovf) base = atomicAdd(P.temp_count, (unsigned long long)tile_total);
+        TileDesc d;
+        d.count = tile_total;
+        d.overflow = ovf;
+        d.temp_base = base;
+        *reinterpret_cast<uint4 *>(P.tile_desc + tile) = *reinterpret_cast<const uint4 *>(&d);
         if (ovf) P.redo_list[atomicAdd(P.redo_count, 1u)] = tile;
       }
+      base = __shfl_sync(kFull, base, 0);
+      // (when temp[] is too small the entries are dropped; the host sees total > capacity and
+      // repeats the call with the exact size)
+      if (!ovf && tile_total && base + tile_total <= P.temp_cap) {
+        const uint32_t *set = L.staging + (size_t)b * kTileChunks * cap;
+        for (uint32_t ci = 0; ci < (uint32_t)kTileChunks; ++ci) {
+          const uint32_t n = __shfl_sync(kFull, c, ci);
+          if (n == 0) continue;
+          uint32_t *dst = P.temp + base + __shfl_sync(kFull, cpre, ci);
+          const uint32_t *st = set + (size_t)ci * cap;
+          for (uint32_t i = lane; i < n; i += 32) dst[i] = st[i];
+        }
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&H.ready[b]);
+      if (lane == 0) {
+        H.ovf[b] = 0;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t *>(&H.drained) = k + 1; // the set may be staged into again
+      }
       if (++s == S) {
         s = 0;
         ph ^= 1;
@@ -771,56 +847,40 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 
   // ================================ scanning warps ================================
   Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
-  uint16_t *my_queue = L.queues + warp * kChunkBytes;
-  const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
-
-  auto copy_out = [&](uint32_t j, uint32_t wc) { // tile iteration j, this warp's staged matches
-    const uint32_t b = j & 1;
-    mbar_wait(&H.ready[b], (j >> 1) & 1u);
-    if (H.ovf_final[b]) return; // the redo pass writes this tile
-    const unsigned long long base = H.base[b] + H.wpre[b][warp];
-    const TileOut to = H.tout[b];
-    const uint32_t *map = use_map ? P.map + (size_t)to.win * kWindowBytes : nullptr;
-    const uint32_t *st = L.staging + ((size_t)b * kScanWarps + warp) * cap;
-    for (uint32_t i = lane; i < wc; i += 32) {
-      const uint32_t e = st[i];
-      const unsigned long long r = base + i;
-      if (r < P.out_cap) sc.write_record(r, to.emit_base, to.p0 + (e >> kPackLenBits), e & ((1u << kPackLenBits) - 1), map);
-    }
-  };
-
-  uint32_t s = 0, ph = 0, prev_wc = 0, k = 0;
-  for (;; ++k) {
-    mbar_wait(&H.full[s], ph);
-    const StageInfo &I = H.info[s];
+  uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
+  unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
+  for (;;) {
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(&H.chunk_ctr, 1u);
+    c = __shfl_sync(kFull, c, 0);
+    const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
+    const uint32_t s = k % S, gen = k / S;
+    const StageInfo &I = H.info[k % kInfoRing];
+    // the mbarrier only tells two phases apart: make sure the stage is in OUR generation first
+    while (ld_volatile_shared(&I.seq) != k) __nanosleep(32);
+    mbar_wait(&H.full[s], gen & 1u);
     if (I.tile == kNoTile) break;
+    const uint32_t b = k % NB;
+    if (k >= NB) { // the staging set must have been copied out (tile k - NB)
+      while ((int)(ld_volatile_shared(&H.drained) - (k - NB + 1)) < 0) __nanosleep(32);
+      __threadfence_block();
+    }
     TileCtx T;
     tile_ctx(I, L.ring + (size_t)s * kStageBytes, T);
-    const uint32_t b = k & 1;
-    uint32_t *my_stage = L.staging + ((size_t)b * kScanWarps + warp) * cap;
-
-    uint32_t wc = 0;
-    for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
-      const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
-      if (cbase >= T.nscan) break;
-      wc += sc.template scan_chunk<kStageMode>(T, cbase, lane, my_stage, wc, cap, my_queue, 0, 0, nullptr, &H.ovf[b]);
-    }
-    if (lane == 0) H.wcnt[b][warp] = wc;
+    const uint32_t cbase = ci * kChunkBytes;
+    uint32_t n = 0;
+    if (cbase < T.nscan)
+      n = sc.template scan_chunk<kStageMode>(T, cbase, lane, L.staging + ((size_t)b * kTileChunks + ci) * cap, cap, my_q1,
+                                             my_q2, 0, 0, nullptr, &H.ovf[b]);
+    if (lane == 0) H.ccnt[b][ci] = n;
     __syncwarp();
     if (lane == 0) mbar_arrive(&H.scanned[s]);
-    if (k > 0) copy_out(k - 1, prev_wc);
-    prev_wc = wc;
-    if (++s == S) {
-      s = 0;
-      ph ^= 1;
-    }
   }
-  if (k > 0) copy_out(k - 1, prev_wc);
   sc.flush_stats(lane);
 }
 
-// Tiles of the redo list, one CTA per tile at a time: count per warp, prefix, then evaluate
-// again writing final records.  The tile's base is the inclusive prefix of its predecessor.
+// Tiles of the redo list, one CTA per tile at a time: count per chunk, prefix, then evaluate
+// again writing final records at the tile's base (prefix_kernel).
 template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
 __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -837,7 +897,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
   }
   __syncthreads();
   Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
-  uint16_t *my_queue = L.queues + (warp % kScanWarps) * kChunkBytes;
+  sc.stat_inc = 0; // the main pass has counted these tiles already
+  uint16_t *my_q1 = L.q1 + (warp % kScanWarps) * kChunkBytes;
+  unsigned long long *my_q2 = L.q2 + (warp % kScanWarps) * kQ2Entries;
   const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
   uint32_t ph = 0;
   for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
@@ -849,33 +911,102 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
     tile_ctx(H.info[0], L.ring, T);
     const unsigned long long emit_base = H.info[0].emit_base;
     const uint32_t *map = use_map ? P.map + (size_t)H.info[0].win * kWindowBytes : nullptr;
-    uint32_t wc = 0;
-    if (warp < kScanWarps) {
-      for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
-        const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
-        if (cbase >= T.nscan) break;
-        sc.stat_inc = 0;
-        wc += sc.template scan_chunk<kCountMode>(T, cbase, lane, nullptr, wc, 0, my_queue, 0, 0, nullptr, nullptr);
-        sc.stat_inc = 1;
+    if (warp < kScanWarps)
+      for (uint32_t ci = warp; ci < (uint32_t)kTileChunks; ci += kScanWarps) {
+        uint32_t cnt = 0;
+        if (ci * kChunkBytes < T.nscan)
+          cnt = sc.template scan_chunk<kCountMode>(T, ci * kChunkBytes, lane, nullptr, 0, my_q1, my_q2, 0, 0, nullptr, nullptr);
+        if (lane == 0) H.ccnt[0][ci] = cnt;
       }
-      if (lane == 0) H.wcnt[0][warp] = wc;
-    }
     __syncthreads();
     if (warp < kScanWarps) {
-      unsigned long long base = 0;
-      const long long g = (long long)P.tile_base + tile;
-      if (g > 0) base = P.tile_state[g - 1] & kStateValueMask;
-      for (uint32_t w = 0; w < warp; ++w) base += H.wcnt[0][w];
-      uint32_t done = 0;
-      for (uint32_t it = 0; it < kWarpSpan / kChunkBytes; ++it) {
-        const uint32_t cbase = warp * kWarpSpan + it * kChunkBytes;
-        if (cbase >= T.nscan) break;
-        sc.stat_inc = 0; // the main pass has counted this tile already
-        done += sc.template scan_chunk<kDirectMode>(T, cbase, lane, nullptr, done, 0, my_queue, base, emit_base, map, nullptr);
-        sc.stat_inc = 1;
+      const unsigned long long tile_base = P.out_base[tile];
+      for (uint32_t ci = warp; ci < (uint32_t)kTileChunks; ci += kScanWarps) {
+        if (ci * kChunkBytes >= T.nscan) break;
+        unsigned long long base = tile_base;
+        for (uint32_t j = 0; j < ci; ++j) base += H.ccnt[0][j];
+        sc.template scan_chunk<kDirectMode>(T, ci * kChunkBytes, lane, nullptr, 0, my_q1, my_q2, base, emit_base, map, nullptr);
       }
     }
-    __syncthreads(); // the stage buffer and wcnt are reused by the next entry
+    __syncthreads(); // the stage buffer and ccnt are reused by the next entry
+  }
+}
+
+// Exclusive prefix over the tile counts of a launch, continuing from *P.total (matches of
+// earlier launches of the same call); one CTA, 4 tiles per thread and step.
+constexpr int kPrefixThreads = 1024;
+__global__ void __launch_bounds__(kPrefixThreads, 1) prefix_kernel(const __grid_constant__ ScanParams P) {
+  __shared__ unsigned long long s_warp[kPrefixThreads / 32];
+  __shared__ unsigned long long s_carry;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = *P.total;
+  __syncthreads();
+  for (uint32_t t0 = 0; t0 < P.num_tiles; t0 += kPrefixThreads * 4) {
+    const uint32_t first = t0 + tid * 4;
+    uint32_t c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = first + i < P.num_tiles ? P.tile_desc[first + i].count : 0u;
+    const unsigned long long mine = (unsigned long long)c[0] + c[1] + c[2] + c[3];
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long before = s_carry;
+    for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+    unsigned long long run = before + incl - mine;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (first + i < P.num_tiles) P.out_base[first + i] = run;
+      run += c[i];
+    }
+    __syncthreads();
+    if (tid == kPrefixThreads - 1) s_carry = run;
+    __syncthreads();
+  }
+  if (tid == 0) *P.total = s_carry;
+}
+
+// Packed entries of temp[] -> final records.  A warp takes 32 tiles at a time (coalesced
+// descriptor reads) and copies the tiles that have matches one after the other.
+constexpr int kPlaceThreads = 256;
+__global__ void __launch_bounds__(kPlaceThreads) place_kernel(const __grid_constant__ ScanParams P) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = gridDim.x * (kPlaceThreads / 32);
+  const uint32_t gw = blockIdx.x * (kPlaceThreads / 32) + (threadIdx.x >> 5);
+  const bool use_map = (P.flags & kWindowMode) && !(P.flags & kIdentityMap);
+  for (uint32_t t0 = gw * 32; t0 < P.num_tiles; t0 += warps * 32) {
+    const uint32_t t = t0 + lane;
+    TileDesc d;
+    d.count = 0;
+    d.overflow = 0;
+    d.temp_base = 0;
+    unsigned long long ob = 0;
+    if (t < P.num_tiles) {
+      *reinterpret_cast<uint4 *>(&d) = __ldg(reinterpret_cast<const uint4 *>(P.tile_desc + t));
+      ob = P.out_base[t];
+    }
+    uint32_t todo = __ballot_sync(kFull, d.count != 0 && d.overflow == 0);
+    while (todo) {
+      const uint32_t src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t n = __shfl_sync(kFull, d.count, src);
+      const unsigned long long tb = __shfl_sync(kFull, d.temp_base, src);
+      const unsigned long long base = __shfl_sync(kFull, ob, src);
+      if (tb + n > P.temp_cap) continue; // dropped entries: the call is repeated with a larger buffer
+      StageInfo I;
+      fill_tile(P, t0 + src, I);
+      const uint32_t *map = use_map ? P.map + (size_t)I.win * kWindowBytes : nullptr;
+      for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t e = __ldg(P.temp + tb + i);
+        const unsigned long long r = base + i;
+        if (r < P.out_cap)
+          put_record(P, r, I.emit_base, I.p0 + (e >> kPackLenBits), e & ((1u << kPackLenBits) - 1), map);
+      }
+    }
   }
 }
 
@@ -885,7 +1016,12 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
   scan_kernel<G, Q, C><<<grid, kScanThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, 1, 0), stream>>>(p);
+  prefix_kernel<<<1, kPrefixThreads, 0, stream>>>(p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  const uint32_t place_blocks = (p.num_tiles + 32 * (kPlaceThreads / 32) - 1) / (32 * (kPlaceThreads / 32));
+  place_kernel<<<place_blocks < 4u * (uint32_t)sms ? place_blocks : 4u * (uint32_t)sms, kPlaceThreads, 0, stream>>>(p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, 1, 0, 0), stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -898,23 +1034,27 @@ cudaError_t configure_variant(size_t smem_limit) {
 
 } // namespace
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t stage_cap) {
-  return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 +
-         size_t(2) * kScanWarps * stage_cap * 4 + kQueueBytes;
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t sets, uint32_t chunk_cap) {
+  return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kQ2Bytes +
+         size_t(sets) * kTileChunks * chunk_cap * 4 + kQ1Bytes;
 }
 
-uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *stage_cap) {
+ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
+  ScanGeometry g;
   for (uint32_t s = kMaxStages; s >= 2; --s) {
-    if (scan_smem_bytes(st, s, kStageCapMin) > smem_limit) continue;
-    // whatever shared memory is left goes to the staging areas (denser matches before a tile
-    // has to be redone)
-    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
-    uint32_t cap = uint32_t(spare / (size_t(2) * kScanWarps * 4)) & ~31u;
-    if (cap > kStageCapMax) cap = kStageCapMax;
-    *stage_cap = cap;
-    return s;
+    // at least as many staging sets as ring stages, capped; whatever is left goes to the
+    // staging capacity (denser matches before a tile has to be redone)
+    const uint32_t sets = s < 3 ? 2 : 3; // never more than stages (see the finisher's wait on `scanned`)
+    if (scan_smem_bytes(st, s, sets, kChunkCapMin) > smem_limit) continue;
+    const size_t spare = smem_limit - scan_smem_bytes(st, s, sets, 0);
+    uint32_t cap = uint32_t(spare / (size_t(sets) * kTileChunks * 4)) & ~7u;
+    if (cap > kChunkCapMax) cap = kChunkCapMax;
+    g.stages = s;
+    g.sets = sets;
+    g.chunk_cap = cap;
+    return g;
   }
-  return 0;
+  return g;
 }
 
 cudaError_t scan_configure(size_t smem_limit) {
@@ -927,9 +1067,9 @@ cudaError_t scan_configure(size_t smem_limit) {
 }
 
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches) {
-  const size_t smem = scan_smem_bytes(p.st, p.stages, p.stage_cap);
+  const size_t smem = scan_smem_bytes(p.st, p.stages, p.sets, p.chunk_cap);
   const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0, c = g && !q && p.st.cls.run != 0;
-  if (launches) *launches += 2;
+  if (launches) *launches += 4;
   if (g && q) return launch_variant<true, true, false>(p, sms, smem, stream);
   if (c) return launch_variant<true, false, true>(p, sms, smem, stream);
   if (g) return launch_variant<true, false, false>(p, sms, smem, stream);

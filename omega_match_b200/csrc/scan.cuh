@@ -38,21 +38,26 @@ enum ScanFlags : uint32_t {
 };
 
 // Geometry of the kernel (compile-time; DESIGN.md "scan kernel").
-constexpr int kScanWarps = 16;                      // warps that scan
-constexpr int kScanThreads = (kScanWarps + 1) * 32; // + one control warp (TMA producer, look-back)
+constexpr int kScanWarps = 30;                      // warps that scan
+constexpr int kScanThreads = 1024;                  // + finisher warp (30: look-back, copy-out) + producer warp (31: TMA)
 constexpr int kTileBytes = 16384;                   // positions per tile
 constexpr int kTilePre = 16;                        // bytes staged in front of a tile (previous byte)
 constexpr int kTileHalo = 112;                      // bytes staged behind a tile
 constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 16512 = 129*128
-constexpr int kWarpSpan = kTileBytes / kScanWarps;  // 1024 positions per warp and tile
-constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes
-constexpr int kMaxStages = 4;
-constexpr uint32_t kStageCapMin = 64;               // staged matches per warp and tile: at least ...
-constexpr uint32_t kStageCapMax = 1024;             // ... at most
-constexpr int kQueueBytes = kScanWarps * kChunkBytes * 2; // candidate queue: u16 per position of a chunk
-constexpr int kSmemHeader = 1024;                   // barriers, per-tile bookkeeping, stage infos
+constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes: the unit a warp grabs
+constexpr int kTileChunks = kTileBytes / kChunkBytes; // 32: one per lane of the finisher warp
+constexpr int kMaxStages = 4;                       // ring of tile buffers
+constexpr int kMaxSets = 4;                         // staging sets (tiles whose matches wait for their base)
+constexpr int kInfoRing = 8;                        // >= kMaxStages + kMaxSets
+constexpr uint32_t kChunkCapMin = 32;               // staged matches per chunk: at least ...
+constexpr uint32_t kChunkCapMax = 512;              // ... at most
+constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
+constexpr int kQ2Entries = 64;                      // hit queue per warp (u64 entries)
+constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
+constexpr int kSmemHeader = 2048;                   // barriers, per-tile bookkeeping, stage infos
 constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
 
+struct TileDesc;
 struct ScanParams {
   DeviceStore st;
   // input bytes
@@ -72,27 +77,45 @@ struct ScanParams {
   uint32_t tiles_per_win;
   // tiles
   uint32_t num_tiles;             // tiles of this launch
-  uint32_t tile_base;             // global index of this launch's first tile in tile_state[]
-  unsigned long long *tile_state; // decoupled look-back descriptors
+  TileDesc *tile_desc;            // [num_tiles] written by the scan, completed by the prefix kernel
+  uint32_t *temp;                 // packed matches (pos_in_tile << 18 | len), one run per tile
+  unsigned long long temp_cap;    // entries
+  unsigned long long *temp_count; // bump allocator of temp[] (may run past temp_cap: entries are then dropped)
   unsigned int *ticket;           // dynamic tile counter of this launch
   // tiles whose matches did not fit the staging area; rewritten by redo_kernel
   uint32_t *redo_list;     // launch-local tile indices
   unsigned int *redo_count;
+  unsigned long long *out_base; // [num_tiles] first result index of each tile (prefix kernel)
   // output
   Record *out;
   uint64_t out_cap;
   uint64_t match_ptr_base;
-  unsigned long long *total;    // inclusive count after the last tile of this launch
+  unsigned long long *total;    // matches so far: start value of this launch's prefix, updated by it
   unsigned long long *counters; // hits, misses, comparisons, long hits (omega_match_stats_t)
   uint32_t flags;
   uint32_t stages;    // ring depth
-  uint32_t stage_cap; // staged matches per warp and tile (two buffers of this size per warp)
+  uint32_t sets;      // staging sets
+  uint32_t chunk_cap; // staged matches per chunk
 };
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t stage_cap);
-// chooses the deepest ring that fits (and the staging capacity); returns 0 if the filters do not fit at all
-uint32_t scan_pick_stages(const DeviceStore &st, size_t smem_limit, uint32_t *stage_cap);
-// main pass followed by the redo pass (which exits at once when no tile overflowed)
+// One per tile.  The scan writes count/overflow/temp_base; prefix_kernel adds out_base, the
+// tile's first index in the result array (matches come out in tile order = offset order).
+struct alignas(16) TileDesc {
+  uint32_t count;    // exact number of matches of the tile
+  uint32_t overflow; // 1: the staging area was too small, redo_kernel writes this tile's records
+  unsigned long long temp_base; // first entry of the tile in temp[]
+};
+
+struct ScanGeometry {
+  uint32_t stages = 0, sets = 0, chunk_cap = 0;
+};
+
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t sets, uint32_t chunk_cap);
+// chooses ring depth, staging sets and capacity for the shared memory there is; stages == 0 if
+// the filters do not fit at all
+ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit);
+// scan -> prefix over the tile counts -> placement of the records in final order -> redo pass
+// (exits at once when no tile overflowed).  `out_base` [num_tiles] is scratch for the prefix.
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches);
 cudaError_t scan_configure(size_t smem_limit);
 
