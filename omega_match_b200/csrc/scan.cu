@@ -56,8 +56,9 @@ constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 
 struct StageInfo { // written by the producer lane, read by everyone after the mbarrier wait
   unsigned long long p0;   // segment-relative position of the tile's first byte
-  unsigned long long len;  // segment length (N, or M_w)
-  unsigned long long end;  // one past the last start position to evaluate
+  uint32_t rem0;           // min(segment length - p0, 2^31): segment bytes from the tile's first position on
+  uint32_t nscan;          // start positions of this tile to evaluate (<= kTileBytes)
+  unsigned long long _pad2;
   long long boff;          // buffer offset of position p0
   unsigned long long emit_base;
   uint32_t tile;           // launch-local tile index, kNoTile = no more work
@@ -601,6 +602,132 @@ struct Scanner {
     return found;
   }
 
+  // The same chunk for the common case -- no position predicate requested, no 1..3 byte
+  // patterns -- written against raw shared-memory offsets with nothing but the essentials in
+  // the per-candidate rounds (the generic scan_chunk above spends ~3x the instructions there).
+  //   sb_off/g4_off/q1_off/q2_off: byte offsets into the CTA's dynamic shared memory.
+  template <int MODE>
+  __device__ __forceinline__ uint32_t scan_chunk_fast(const TileCtx &T, uint8_t *smem_base, uint32_t sb_off,
+                                                      uint32_t g4_off, uint32_t q1_off, uint32_t q2_off,
+                                                      uint32_t cbase, uint32_t lane, uint32_t *stage, uint32_t cap,
+                                                      unsigned long long out_base, unsigned long long emit_base,
+                                                      const uint32_t *map, uint32_t *overflow) const {
+    const uint32_t lpos = cbase + lane * 16;
+    const uint32_t src = sb_off + kTilePre + lpos;
+    const uint4 v = *reinterpret_cast<const uint4 *>(smem_base + src);
+    uint32_t cand = 0;
+    if (HAS_CLS) {
+      const uint2 nx = *reinterpret_cast<const uint2 *>(smem_base + src + 16);
+      uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
+                   (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
+                   (gather4(class_word(nx.y)) << 20);
+      uint32_t have = 1;
+      while (have * 2 <= C.run) {
+        a &= a >> have;
+        have *= 2;
+      }
+      if (have < C.run) a &= a >> (C.run - have);
+      cand = a & 0xFFFFu;
+    } else {
+      const uint32_t w4 = *reinterpret_cast<const uint32_t *>(smem_base + src + 16);
+      const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
+      const uint32_t sh = P.st.g4_shift;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
+        const uint32_t b = (gram * kHashMul) >> sh;
+        const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + g4_off + ((b >> 5) << 2));
+        cand |= ((word >> (b & 31)) & 1u) << k;
+      }
+    }
+    if (lpos + 16 > T.nscan) cand &= lpos >= T.nscan ? 0u : ((1u << (T.nscan - lpos)) - 1u);
+    const uint32_t cnt = __popc(cand);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, incl, d);
+      if (lane >= (uint32_t)d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    if (total == 0) return 0;
+    {
+      uint32_t qa = q1_off + 2u * (incl - cnt);
+      const uint32_t eb = lane * 16 - 1; // __ffs is 1-based
+      while (cand) {
+        *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)(eb + __ffs(cand));
+        cand &= cand - 1;
+        qa += 2;
+      }
+    }
+    __syncwarp();
+    unsigned long long *q2 = reinterpret_cast<unsigned long long *>(smem_base + q2_off);
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t tile_off = sb_off + kTilePre + cbase;
+    const uint32_t key_shift = P.st.key_shift, g4_shift = P.st.g4_shift, empty = P.st.empty_key;
+    const uint4 *keys = P.st.keys;
+    const uint32_t rem_c = T.rem0 - cbase; // >= 1
+    uint32_t found = 0, q2n = 0;
+    for (uint32_t base = 0; base < total; base += 64) {
+      uint32_t e[2], gram[2], bucket[2];
+      bool pass[2];
+      uint4 kb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t idx = base + u * 32 + lane;
+        pass[u] = idx < total;
+        e[u] = pass[u] ? *reinterpret_cast<const uint16_t *>(smem_base + q1_off + 2u * idx) : 0u;
+        const uint32_t a = tile_off + e[u];
+        const uint32_t lo = *reinterpret_cast<const uint32_t *>(smem_base + (a & ~3u));
+        const uint32_t hi = *reinterpret_cast<const uint32_t *>(smem_base + (a & ~3u) + 4);
+        gram[u] = __byte_perm(__funnelshift_r(lo, hi, a << 3), 0, 0x0123);
+        const uint32_t h = gram[u] * kHashMul;
+        pass[u] = pass[u] && (e[u] + 4u <= rem_c);
+        if (HAS_CLS) {
+          const uint32_t b = h >> g4_shift;
+          const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + g4_off + ((b >> 5) << 2));
+          pass[u] = pass[u] && ((word >> (b & 31)) & 1u);
+        }
+        bucket[u] = h >> key_shift;
+        kb[u] = make_uint4(empty, empty, empty, empty);
+        if (pass[u]) kb[u] = __ldg(keys + bucket[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && base + 32 >= total) break;
+        const uint32_t g = gram[u];
+        bool hit = pass[u] && (kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g);
+        // rare: the home bucket is full and does not hold the gram -> next bucket(s)
+        if (__any_sync(kFull, pass[u] && !hit && kb[u].w != empty)) {
+          while (pass[u] && !hit && kb[u].w != empty) {
+            bucket[u] = (bucket[u] + 1) & P.st.key_mask;
+            kb[u] = __ldg(keys + bucket[u]);
+            hit = kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g;
+          }
+        }
+        const uint32_t bal = __ballot_sync(kFull, hit);
+        if (!bal) continue;
+        if (hit) {
+          const uint32_t place = kb[u].x == g ? 0u : kb[u].y == g ? 1u : kb[u].z == g ? 2u : 3u;
+          q2[q2n + __popc(bal & lt)] = ((unsigned long long)(cbase + e[u]) << 32) | (4u * bucket[u] + place);
+        }
+        q2n += __popc(bal);
+        __syncwarp();
+        if (q2n >= 32) {
+          found += verify_batch<MODE>(T, q2, 32, lane, stage, found, cap, out_base, emit_base, map, overflow);
+          const uint32_t rest = q2n - 32;
+          const unsigned long long mv = lane < rest ? q2[32 + lane] : 0ull;
+          __syncwarp();
+          if (lane < rest) q2[lane] = mv;
+          __syncwarp();
+          q2n = rest;
+        }
+      }
+    }
+    if (q2n) found += verify_batch<MODE>(T, q2, q2n, lane, stage, found, cap, out_base, emit_base, map, overflow);
+    __syncwarp();
+    return found;
+  }
+
   __device__ __forceinline__ void write_record(unsigned long long r, unsigned long long emit_base,
                                                unsigned long long pos, uint32_t len, const uint32_t *map) const {
     put_record(P, r, emit_base, pos, len, map);
@@ -628,34 +755,40 @@ struct Scanner {
 __device__ __forceinline__ void fill_tile(const ScanParams &P, uint32_t t, StageInfo &I) {
   I.tile = t;
   uint32_t win = 0;
+  unsigned long long len, end;
   if (P.flags & kWindowMode) {
     win = t / P.tiles_per_win;
     const WindowDesc wd = P.windows[win];
     I.p0 = (unsigned long long)(t % P.tiles_per_win) * kTileBytes;
-    I.len = wd.norm_len;
-    I.end = wd.norm_len;
+    len = wd.norm_len;
+    end = wd.norm_len;
     I.boff = (long long)(P.win_buf_off + (unsigned long long)win * P.win_stride + I.p0);
     I.tail = wd.tail;
     I.emit_base = P.win_src_base + (unsigned long long)win * kWindowBytes;
   } else {
     I.p0 = P.scan_begin + (unsigned long long)t * kTileBytes;
-    I.len = P.seg_len;
-    I.end = P.scan_end < P.seg_len ? P.scan_end : P.seg_len;
+    len = P.seg_len;
+    end = P.scan_end < P.seg_len ? P.scan_end : P.seg_len;
     I.boff = P.seg_buf_off + (long long)I.p0;
     I.tail = P.tail_byte;
     I.emit_base = 0;
   }
   I.win = win;
   I.staged = 0;
-  if (I.p0 < I.end) {
+  I.rem0 = 0;
+  I.nscan = 0;
+  if (I.p0 < end) {
     long long e = I.boff + kTileBytes + kTileHalo;
     if (e > (long long)P.buf_len) e = (long long)P.buf_len;
     I.staged = (uint32_t)(e - I.boff);
+    const unsigned long long left = len - I.p0, ns = end - I.p0;
+    I.rem0 = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;
+    I.nscan = ns > (unsigned long long)kTileBytes ? (uint32_t)kTileBytes : (uint32_t)ns;
   }
 }
 // ... and starts its bulk copy into `dst` (a stage buffer), completing on `bar`.
 __device__ __forceinline__ void copy_tile(const ScanParams &P, const StageInfo &I, uint8_t *dst, uint64_t *bar) {
-  if (I.p0 < I.end) {
+  if (I.nscan) {
     const long long pre = I.boff >= kTilePre ? kTilePre : 0;
     const uint32_t bytes = (uint32_t)(I.staged + pre);
     mbar_expect_tx(bar, bytes);
@@ -673,10 +806,8 @@ __device__ __forceinline__ void tile_ctx(const StageInfo &I, const uint8_t *sb, 
   T.sb = sb;
   T.p0 = I.p0;
   T.boff = I.boff;
-  const unsigned long long left = I.len - I.p0;
-  T.rem0 = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;
-  const unsigned long long ns = I.end > I.p0 ? I.end - I.p0 : 0;
-  T.nscan = ns > (unsigned long long)kTileBytes ? (uint32_t)kTileBytes : (uint32_t)ns;
+  T.rem0 = I.rem0;
+  T.nscan = I.nscan;
   T.staged = I.staged;
   T.tail = I.tail;
   T.first = I.p0 == 0;
@@ -720,7 +851,7 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t S = P.stages, NB = P.sets, cap = P.chunk_cap;
@@ -849,18 +980,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
   uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
   unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
+  const uint32_t ring_off = (uint32_t)(L.ring - smem), g4_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
+  const uint32_t q1_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q1) - smem);
+  const uint32_t q2_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q2) - smem);
   for (;;) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(&H.chunk_ctr, 1u);
     c = __shfl_sync(kFull, c, 0);
     const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
-    const uint32_t s = k % S, gen = k / S;
+    const uint32_t s = k & (S - 1), gen = k >> (S == 4 ? 2 : 1); // S is 2 or 4
     const StageInfo &I = H.info[k % kInfoRing];
     // the mbarrier only tells two phases apart: make sure the stage is in OUR generation first
     while (ld_volatile_shared(&I.seq) != k) __nanosleep(32);
     mbar_wait(&H.full[s], gen & 1u);
     if (I.tile == kNoTile) break;
-    const uint32_t b = k % NB;
+    const uint32_t b = k & (NB - 1); // NB is 2 or 4
     if (k >= NB) { // the staging set must have been copied out (tile k - NB)
       while ((int)(ld_volatile_shared(&H.drained) - (k - NB + 1)) < 0) __nanosleep(32);
       __threadfence_block();
@@ -868,10 +1002,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     TileCtx T;
     tile_ctx(I, L.ring + (size_t)s * kStageBytes, T);
     const uint32_t cbase = ci * kChunkBytes;
+    uint32_t *stage = L.staging + ((size_t)b * kTileChunks + ci) * cap;
     uint32_t n = 0;
-    if (cbase < T.nscan)
-      n = sc.template scan_chunk<kStageMode>(T, cbase, lane, L.staging + ((size_t)b * kTileChunks + ci) * cap, cap, my_q1,
-                                             my_q2, 0, 0, nullptr, &H.ovf[b]);
+    if (cbase < T.nscan) {
+      if (FAST)
+        n = sc.template scan_chunk_fast<kStageMode>(T, smem, ring_off + s * kStageBytes, g4_off, q1_off, q2_off, cbase,
+                                                    lane, stage, cap, 0, 0, nullptr, &H.ovf[b]);
+      else
+        n = sc.template scan_chunk<kStageMode>(T, cbase, lane, stage, cap, my_q1, my_q2, 0, 0, nullptr, &H.ovf[b]);
+    }
     if (lane == 0) H.ccnt[b][ci] = n;
     __syncwarp();
     if (lane == 0) mbar_arrive(&H.scanned[s]);
@@ -1013,7 +1152,13 @@ __global__ void __launch_bounds__(kPlaceThreads) place_kernel(const __grid_const
 template <bool G, bool Q, bool C>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
   const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
-  scan_kernel<G, Q, C><<<grid, kScanThreads, smem, stream>>>(p);
+  // the lean per-candidate path covers: gram patterns only, no position predicate requested
+  constexpr bool can_fast = G && !Q;
+  const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
+  if (fast)
+    scan_kernel<G, Q, C, can_fast><<<grid, kScanThreads, smem, stream>>>(p);
+  else
+    scan_kernel<G, Q, C, false><<<grid, kScanThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   prefix_kernel<<<1, kPrefixThreads, 0, stream>>>(p);
@@ -1027,8 +1172,12 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
 
 template <bool G, bool Q, bool C>
 cudaError_t configure_variant(size_t smem_limit) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
   if (e != cudaSuccess) return e;
+  if (G && !Q) {
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G && !Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    if (e != cudaSuccess) return e;
+  }
   return cudaFuncSetAttribute(redo_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
 }
 
@@ -1041,11 +1190,12 @@ size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t sets, ui
 
 ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
   ScanGeometry g;
-  for (uint32_t s = kMaxStages; s >= 2; --s) {
-    // at least as many staging sets as ring stages, capped; whatever is left goes to the
-    // staging capacity (denser matches before a tile has to be redone)
-    const uint32_t sets = s < 3 ? 2 : 3; // never more than stages (see the finisher's wait on `scanned`)
+  // ring depth and staging sets are powers of two (index by mask), sets <= stages (see the
+  // finisher's wait on `scanned`), stages + sets <= kInfoRing
+  for (uint32_t s = kMaxStages; s >= 2; s >>= 1) {
+    const uint32_t sets = s;
     if (scan_smem_bytes(st, s, sets, kChunkCapMin) > smem_limit) continue;
+    // whatever is left goes to the staging capacity (denser matches before a tile is redone)
     const size_t spare = smem_limit - scan_smem_bytes(st, s, sets, 0);
     uint32_t cap = uint32_t(spare / (size_t(sets) * kTileChunks * 4)) & ~7u;
     if (cap > kChunkCapMax) cap = kChunkCapMax;

@@ -29,3 +29,16 @@ for l in sorted(lines, key=lambda l: -l[3])[:top]:
 print("-- by stall samples")
 for l in sorted(lines, key=lambda l: -l[4])[:top]:
     print(f"  samp={100*l[4]/ts:5.2f}% exec={100*l[3]/ti:5.2f}% thr={l[5]:>5s} {l[0]}:{l[1]:<4d} {l[2][:100]}")
+if "--ranges" in sys.argv:
+    import re
+    spec = sys.argv[sys.argv.index("--ranges") + 1]  # "name:lo-hi,name:lo-hi"
+    print("-- by line range (scan.cu)")
+    for part in spec.split(","):
+        name, rng = part.split(":")
+        lo, hi = map(int, rng.split("-"))
+        e = sum(l[3] for l in lines if l[0] == "scan.cu" and lo <= l[1] <= hi)
+        sm = sum(l[4] for l in lines if l[0] == "scan.cu" and lo <= l[1] <= hi)
+        print(f"  {name:16s} exec={100*e/ti:5.2f}% samp={100*sm/ts:5.2f}%")
+    e = sum(l[3] for l in lines if l[0] != "scan.cu")
+    sm = sum(l[4] for l in lines if l[0] != "scan.cu")
+    print(f"  {'other files':16s} exec={100*e/ti:5.2f}% samp={100*sm/ts:5.2f}%")
