@@ -77,6 +77,7 @@ struct SmemHeader {
   uint32_t chunk_ctr; // next chunk of the CTA's tile sequence
   uint32_t drained;   // tiles whose staged matches have been copied out (finisher)
   uint32_t ovf[kMaxSets];
+  uint32_t done[kInfoRing]; // chunks of tile iteration k (entry k % kInfoRing) that have been scanned
   uint32_t ccnt[kMaxSets][kTileChunks];
   StageInfo info[kInfoRing];
 };
@@ -652,11 +653,21 @@ struct Scanner {
     if (total == 0) return 0;
     {
       uint32_t qa = q1_off + 2u * (incl - cnt);
-      const uint32_t eb = lane * 16 - 1; // __ffs is 1-based
-      while (cand) {
-        *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)(eb + __ffs(cand));
-        cand &= cand - 1;
-        qa += 2;
+      if (__any_sync(kFull, cnt > 4)) { // dense: 16 predicated steps, no branches
+        const uint32_t eb = lane * 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if ((cand >> k) & 1u) {
+            *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)(eb + k);
+            qa += 2;
+          }
+      } else {
+        const uint32_t eb = lane * 16 - 1; // __ffs is 1-based
+        while (cand) {
+          *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)(eb + __ffs(cand));
+          cand &= cand - 1;
+          qa += 2;
+        }
       }
     }
     __syncwarp();
@@ -870,7 +881,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     H.chunk_ctr = 0;
     H.drained = 0;
     for (uint32_t b = 0; b < kMaxSets; ++b) H.ovf[b] = 0;
-    for (uint32_t i = 0; i < kInfoRing; ++i) H.info[i].seq = kNoTile;
+    for (uint32_t i = 0; i < kInfoRing; ++i) {
+      H.info[i].seq = kNoTile;
+      H.done[i] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -915,7 +929,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 
   if (warp == kScanWarps) {
     // ============ finisher warp: tile descriptor + staged matches -> temp[] ============
-    uint32_t s = 0, ph = 0;
     for (uint32_t k = 0;; ++k) {
       const StageInfo &I = H.info[k % kInfoRing];
       // (no wait on `full` here: the finisher may lag the producer by more than one
@@ -924,9 +937,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       __threadfence_block();
       const uint32_t tile = I.tile;
       if (tile == kNoTile) break;
-      // sets <= stages (scan_pick_geometry), so tile k + S cannot be scanned before tile k has
-      // been finished: this wait is never more than one generation behind
-      mbar_wait(&H.scanned[s], ph);
+      // all chunks scanned?  (a counter, not the `scanned` mbarrier: with more staging sets
+      // than ring stages the finisher may be several generations of the stage behind)
+      while (ld_volatile_shared(&H.done[k % kInfoRing]) != (uint32_t)kTileChunks) __nanosleep(32);
+      __threadfence_block();
       const uint32_t b = k % NB;
       // chunk totals -> exclusive prefixes (lane = chunk)
       const uint32_t c = H.ccnt[b][lane];
@@ -965,12 +979,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) {
         H.ovf[b] = 0;
+        H.done[k % kInfoRing] = 0;
         __threadfence_block();
         *reinterpret_cast<volatile uint32_t *>(&H.drained) = k + 1; // the set may be staged into again
-      }
-      if (++s == S) {
-        s = 0;
-        ph ^= 1;
       }
     }
     return;
@@ -1011,9 +1022,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       else
         n = sc.template scan_chunk<kStageMode>(T, cbase, lane, stage, cap, my_q1, my_q2, 0, 0, nullptr, &H.ovf[b]);
     }
-    if (lane == 0) H.ccnt[b][ci] = n;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&H.scanned[s]);
+    if (lane == 0) {
+      H.ccnt[b][ci] = n;
+      mbar_arrive(&H.scanned[s]); // producer: the stage buffer is not read any more (release)
+      __threadfence_block();
+      atomicAdd(&H.done[k % kInfoRing], 1u); // finisher: staged matches and count are in place
+    }
   }
   sc.flush_stats(lane);
 }
@@ -1190,14 +1205,17 @@ size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t sets, ui
 
 ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
   ScanGeometry g;
-  // ring depth and staging sets are powers of two (index by mask), sets <= stages (see the
-  // finisher's wait on `scanned`), stages + sets <= kInfoRing
+  // ring depth and staging sets are powers of two (indexed by mask); stages + sets <= kInfoRing
   for (uint32_t s = kMaxStages; s >= 2; s >>= 1) {
-    const uint32_t sets = s;
-    if (scan_smem_bytes(st, s, sets, kChunkCapMin) > smem_limit) continue;
-    // whatever is left goes to the staging capacity (denser matches before a tile is redone)
-    const size_t spare = smem_limit - scan_smem_bytes(st, s, sets, 0);
-    uint32_t cap = uint32_t(spare / (size_t(sets) * kTileChunks * 4)) & ~7u;
+    if (scan_smem_bytes(st, s, 2, kChunkCapMin) > smem_limit) continue;
+    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0, 0);
+    auto cap_for = [&](uint32_t sets) { return uint32_t(spare / (size_t(sets) * kTileChunks * 4)) & ~7u; };
+    // more sets = scanning warps run further ahead of the finisher; more capacity = denser
+    // matches before a tile has to be redone
+    uint32_t sets = 2;
+    if (cap_for(8) >= 64) sets = 8;
+    else if (cap_for(4) >= 32) sets = 4;
+    uint32_t cap = cap_for(sets);
     if (cap > kChunkCapMax) cap = kChunkCapMax;
     g.stages = s;
     g.sets = sets;

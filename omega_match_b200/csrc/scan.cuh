@@ -47,14 +47,14 @@ constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 16512 = 129*12
 constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes: the unit a warp grabs
 constexpr int kTileChunks = kTileBytes / kChunkBytes; // 32: one per lane of the finisher warp
 constexpr int kMaxStages = 4;                       // ring of tile buffers
-constexpr int kMaxSets = 4;                         // staging sets (tiles whose matches wait for their base)
-constexpr int kInfoRing = 8;                        // >= kMaxStages + kMaxSets
-constexpr uint32_t kChunkCapMin = 32;               // staged matches per chunk: at least ...
+constexpr int kMaxSets = 8;                         // staging sets (tiles whose matches wait for the finisher)
+constexpr int kInfoRing = 16;                       // >= kMaxStages + kMaxSets
+constexpr uint32_t kChunkCapMin = 16;               // staged matches per chunk: at least ...
 constexpr uint32_t kChunkCapMax = 512;              // ... at most
 constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
 constexpr int kQ2Entries = 64;                      // hit queue per warp (u64 entries)
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
-constexpr int kSmemHeader = 2048;                   // barriers, per-tile bookkeeping, stage infos
+constexpr int kSmemHeader = 3072;                   // barriers, per-tile bookkeeping, stage infos
 constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
 
 struct TileDesc;
