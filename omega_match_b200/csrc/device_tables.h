@@ -63,6 +63,9 @@ struct ByteClass {
   uint32_t and_mask = 0; // 0x7f or 0x5f
   uint32_t n_ranges = 0; // 1 or 2
   uint32_t lo[2] = {0, 0}, hi[2] = {0, 0};
+  // the same, replicated into the four bytes of a word for the kernel's SWAR test (store.cpp):
+  // and4 = and_mask * 0x01010101, addlo[i] = (0x80 - lo[i]) * 0x01010101, addhi[i] = (0x7f - hi[i]) * 0x01010101
+  uint32_t and4 = 0, addlo[2] = {0, 0}, addhi[2] = {0, 0};
 };
 
 // Everything the scan kernel needs to know about the store; passed by value.

@@ -244,11 +244,13 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   if (windowed) fl |= kWindowMode;
   if (identity_map) fl |= kIdentityMap;
 
-  unsigned long long total = 0;
-  for (int attempt = 0; attempt < 3; ++attempt) {
+  unsigned long long total = 0, temp_used = 0;
+  uint64_t temp_extra = 0; // grows when the block allocator of temp[] wasted more than the slack
+  for (int attempt = 0; attempt < 4; ++attempt) {
     if (E.out.ensure(cap * sizeof(Record))) return -1;
     cap = E.out.cap / sizeof(Record);
-    if (E.temp.ensure(cap * 4)) return -1;
+    const uint64_t temp_cap = cap + cap / 2 + kTempSlackPerSm * uint64_t(E.sms) * n_batches + temp_extra;
+    if (E.temp.ensure(temp_cap * 4)) return -1;
     OLM_CUDA(cudaMemsetAsync(d_tickets, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_redo_counts, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_total, 0, 128, E.stream));
@@ -260,7 +262,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.tile_desc = static_cast<TileDesc *>(E.tile_desc.p);
     P.out_base = static_cast<unsigned long long *>(E.tile_out.p);
     P.temp = static_cast<uint32_t *>(E.temp.p);
-    P.temp_cap = cap;
+    P.temp_cap = temp_cap;
     P.temp_count = d_temp_count;
     P.out = static_cast<Record *>(E.out.p);
     P.out_cap = cap;
@@ -322,16 +324,18 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     }
     OLM_CUDA(cudaEventRecord(E.ev[1], E.stream));
     OLM_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, E.stream));
+    OLM_CUDA(cudaMemcpyAsync(&temp_used, d_temp_count, sizeof temp_used, cudaMemcpyDeviceToHost, E.stream));
     OLM_CUDA(cudaMemcpyAsync(E.counters, d_counters, sizeof E.counters, cudaMemcpyDeviceToHost, E.stream));
     OLM_CUDA(cudaStreamSynchronize(E.stream));
     E.last.kernel_launches = launches;
     E.last.scan_launches = scan_launches;
-    if (total <= cap) break;
-    if (attempt == 2) {
+    if (total <= cap && temp_used <= temp_cap) break;
+    if (temp_used > temp_cap) temp_extra += temp_used - temp_cap + temp_used / 8;
+    if (attempt == 3) {
       std::fprintf(stderr, "libomega_match(b200): result buffer still too small after retry\n");
       return -1;
     }
-    cap = total + total / 16 + 4096; // exact count is known now
+    if (total > cap) cap = total + total / 16 + 4096; // exact count is known now
   }
   E.out_hint = std::max<uint64_t>(E.out_hint, total + total / 8);
   E.last.matches_before_filter = total;

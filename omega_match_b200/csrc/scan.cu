@@ -53,6 +53,7 @@ namespace {
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+constexpr unsigned long long kTempBlock = 4096; // entries of temp[] a CTA reserves at a time
 
 struct StageInfo { // written by the producer lane, read by everyone after the mbarrier wait
   unsigned long long p0;   // segment-relative position of the tile's first byte
@@ -76,6 +77,7 @@ struct SmemHeader {
   uint64_t scanned[kMaxStages];
   uint32_t chunk_ctr; // next chunk of the CTA's tile sequence
   uint32_t drained;   // tiles whose staged matches have been copied out (finisher)
+  uint32_t end_k;     // first tile iteration without a tile (kNoTile until the tickets run out)
   uint32_t ovf[kMaxSets];
   uint32_t done[kInfoRing]; // chunks of tile iteration k (entry k % kInfoRing) that have been scanned
   uint32_t ccnt[kMaxSets][kTileChunks];
@@ -161,19 +163,12 @@ __device__ __forceinline__ void put_record(const ScanParams &P, unsigned long lo
 
 enum ChunkMode { kStageMode = 0, kCountMode = 1, kDirectMode = 2 };
 
-// SWAR constants of the byte-class prefilter (device_tables.h ByteClass), replicated per byte
-struct ClassRegs {
-  uint32_t and4, addlo0, addhi0, addlo1, addhi1, run;
-  bool two;
-};
-
 template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
 struct Scanner {
   const ScanParams &P;
   const uint32_t *g4s;
   const uint32_t *p23s;
   const uint32_t fl;
-  ClassRegs C;
   // statistics of omega_match_stats_t that cost nothing extra (list_matcher.h:43-49):
   // hits = buckets found + short matches accepted, misses = short candidates rejected by a
   // predicate, comparisons = bucket patterns that fit (matcher.c:783-799, :818-877, :210)
@@ -181,16 +176,7 @@ struct Scanner {
   mutable uint32_t stat_inc = 1; // 0 while a position is evaluated a second time
 
   __device__ __forceinline__ Scanner(const ScanParams &p, const uint32_t *g4, const uint32_t *p23)
-      : P(p), g4s(g4), p23s(p23), fl(p.flags) {
-    const ByteClass &c = p.st.cls;
-    C.and4 = c.and_mask * 0x01010101u;
-    C.addlo0 = (0x80u - c.lo[0]) * 0x01010101u;
-    C.addhi0 = (0x7Fu - c.hi[0]) * 0x01010101u;
-    C.addlo1 = (0x80u - c.lo[1]) * 0x01010101u;
-    C.addhi1 = (0x7Fu - c.hi[1]) * 0x01010101u;
-    C.two = c.n_ranges > 1;
-    C.run = c.run;
-  }
+      : P(p), g4s(g4), p23s(p23), fl(p.flags) {}
 
   __device__ __forceinline__ uint32_t hay_byte(const TileCtx &T, uint32_t rel) const {
     if (rel < T.staged) return T.sb[kTilePre + rel];
@@ -319,10 +305,12 @@ struct Scanner {
           n_long_hits += stat_inc;
         }
         // bytes 4..11 of a pattern of length len against the haystack
+        const unsigned long long hay48 = ((unsigned long long)hay8 << 32) | hay4;
         auto head_equal = [&](uint32_t len, uint32_t n4, uint32_t n8) {
-          const uint32_t m4 = len >= 8 ? kFull : ((1u << ((len - 4) * 8)) - 1u);
-          const uint32_t m8 = len >= 12 ? kFull : (len > 8 ? ((1u << ((len - 8) * 8)) - 1u) : 0u);
-          return (((hay4 ^ n4) & m4) | ((hay8 ^ n8) & m8)) == 0;
+          // the first min(len, 12) - 4 bytes of the 8-byte window, via one 64-bit shift
+          const uint32_t drop = len >= 12 ? 0u : (12u - len) * 8u; // bits of the window beyond the pattern
+          const unsigned long long diff = (hay48 ^ (((unsigned long long)n8 << 32) | n4)) << drop;
+          return diff == 0;
         };
         if (meta & kSlotMulti) {
           const uint32_t cnt = meta & kSlotValueMask;
@@ -411,9 +399,10 @@ struct Scanner {
 
   // class prefilter: bit 7 of every byte of the result = byte is in the class
   __device__ __forceinline__ uint32_t class_word(uint32_t w) const {
-    const uint32_t t = w & C.and4;
-    uint32_t in = (t + C.addlo0) & ~(t + C.addhi0);
-    if (C.two) in |= (t + C.addlo1) & ~(t + C.addhi1);
+    const ByteClass &c = P.st.cls;
+    const uint32_t t = w & c.and4;
+    uint32_t in = (t + c.addlo[0]) & ~(t + c.addhi[0]);
+    if (c.n_ranges > 1) in |= (t + c.addlo[1]) & ~(t + c.addhi[1]);
     return in & ~w & 0x80808080u;
   }
   // bits 7,15,23,31 -> bits 0..3
@@ -433,11 +422,11 @@ struct Scanner {
                    (gather4(class_word(nx.y)) << 20);
       // bit i = bytes lpos+i .. lpos+i+run-1 are all in the class (run <= 8, i < 16)
       uint32_t have = 1;
-      while (have * 2 <= C.run) {
+      while (have * 2 <= P.st.cls.run) {
         a &= a >> have;
         have *= 2;
       }
-      if (have < C.run) a &= a >> (C.run - have);
+      if (have < P.st.cls.run) a &= a >> (P.st.cls.run - have);
       cg = a & 0xFFFFu;
       return;
     }
@@ -623,11 +612,11 @@ struct Scanner {
                    (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
                    (gather4(class_word(nx.y)) << 20);
       uint32_t have = 1;
-      while (have * 2 <= C.run) {
+      while (have * 2 <= P.st.cls.run) {
         a &= a >> have;
         have *= 2;
       }
-      if (have < C.run) a &= a >> (C.run - have);
+      if (have < P.st.cls.run) a &= a >> (P.st.cls.run - have);
       cand = a & 0xFFFFu;
     } else {
       const uint32_t w4 = *reinterpret_cast<const uint32_t *>(smem_base + src + 16);
@@ -880,6 +869,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     }
     H.chunk_ctr = 0;
     H.drained = 0;
+    H.end_k = kNoTile;
     for (uint32_t b = 0; b < kMaxSets; ++b) H.ovf[b] = 0;
     for (uint32_t i = 0; i < kInfoRing; ++i) {
       H.info[i].seq = kNoTile;
@@ -902,6 +892,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
         I.tile = kNoTile;
         __threadfence_block();
         *reinterpret_cast<volatile uint32_t *>(&I.seq) = k;
+        if (k < H.end_k) *reinterpret_cast<volatile uint32_t *>(&H.end_k) = k;
         mbar_expect_tx(&H.full[s], 0);
         return;
       }
@@ -929,6 +920,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 
   if (warp == kScanWarps) {
     // ============ finisher warp: tile descriptor + staged matches -> temp[] ============
+    unsigned long long blk_next = 0, blk_left = 0; // lane 0: this CTA's current block of temp[]
     for (uint32_t k = 0;; ++k) {
       const StageInfo &I = H.info[k % kInfoRing];
       // (no wait on `full` here: the finisher may lag the producer by more than one
@@ -943,7 +935,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       __threadfence_block();
       const uint32_t b = k % NB;
       // chunk totals -> exclusive prefixes (lane = chunk)
-      const uint32_t c = H.ccnt[b][lane];
+      const uint32_t c = lane < (uint32_t)kTileChunks ? H.ccnt[b][lane] : 0u;
       uint32_t incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -955,7 +947,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       const uint32_t ovf = H.ovf[b];
       unsigned long long base = 0;
       if (lane == 0) {
-        if (tile_total && !ovf) base = atomicAdd(P.temp_count, (unsigned long long)tile_total);
+        if (tile_total && !ovf) {
+          // temp[] is handed out in blocks of kTempBlock entries (one global atomic per block,
+          // not per tile); a tile's run never straddles blocks
+          if (tile_total > blk_left) {
+            const unsigned long long want = 4ull * tile_total > kTempBlock ? 4ull * tile_total : kTempBlock;
+            blk_next = atomicAdd(P.temp_count, want);
+            blk_left = want;
+          }
+          base = blk_next;
+          blk_next += tile_total;
+          blk_left -= tile_total;
+        }
         TileDesc d;
         d.count = tile_total;
         d.overflow = ovf;
@@ -1001,8 +1004,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
     const uint32_t s = k & (S - 1), gen = k >> (S == 4 ? 2 : 1); // S is 2 or 4
     const StageInfo &I = H.info[k % kInfoRing];
-    // the mbarrier only tells two phases apart: make sure the stage is in OUR generation first
-    while (ld_volatile_shared(&I.seq) != k) __nanosleep(32);
+    // The mbarrier only tells two phases apart: make sure the stage is in OUR generation first.
+    // (Chunks past the CTA's last tile may belong to an iteration that is never produced.)
+    bool over = false;
+    while (ld_volatile_shared(&I.seq) != k) {
+      if (k >= ld_volatile_shared(&H.end_k)) {
+        over = true;
+        break;
+      }
+      __nanosleep(32);
+    }
+    if (over) break;
     mbar_wait(&H.full[s], gen & 1u);
     if (I.tile == kNoTile) break;
     const uint32_t b = k & (NB - 1); // NB is 2 or 4

@@ -79,7 +79,7 @@ struct ScanParams {
   uint32_t num_tiles;             // tiles of this launch
   TileDesc *tile_desc;            // [num_tiles] written by the scan, completed by the prefix kernel
   uint32_t *temp;                 // packed matches (pos_in_tile << 18 | len), one run per tile
-  unsigned long long temp_cap;    // entries
+  unsigned long long temp_cap;    // entries (>= result capacity + kTempSlackPerSm * SMs: blocks are not filled to the end)
   unsigned long long *temp_count; // bump allocator of temp[] (may run past temp_cap: entries are then dropped)
   unsigned int *ticket;           // dynamic tile counter of this launch
   // tiles whose matches did not fit the staging area; rewritten by redo_kernel
@@ -105,6 +105,8 @@ struct alignas(16) TileDesc {
   uint32_t overflow; // 1: the staging area was too small, redo_kernel writes this tile's records
   unsigned long long temp_base; // first entry of the tile in temp[]
 };
+
+constexpr uint64_t kTempSlackPerSm = 8192; // see scan.cu kTempBlock
 
 struct ScanGeometry {
   uint32_t stages = 0, sets = 0, chunk_cap = 0;

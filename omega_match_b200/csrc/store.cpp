@@ -335,7 +335,14 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
         }
       }
       // worth its instructions only when it lets through a minority of the byte values
-      if (best.run && best_cost / 4 <= 96) d.cls = best;
+      if (best.run && best_cost / 4 <= 96) {
+        best.and4 = best.and_mask * 0x01010101u;
+        for (uint32_t i = 0; i < 2; ++i) {
+          best.addlo[i] = (0x80u - best.lo[i]) * 0x01010101u;
+          best.addhi[i] = (0x7Fu - best.hi[i]) * 0x01010101u;
+        }
+        d.cls = best;
+      }
     }
   }
 
