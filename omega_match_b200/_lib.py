@@ -51,10 +51,16 @@ class CudaTimingC(C.Structure):
 class StoreInfoC(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("flags", "smallest", "largest", "stored_patterns", "table_size",
                                          "occupied_buckets", "len1", "len2", "len3", "len4")] + [
-        ("store_bytes", C.c_uint64), ("file_bytes", C.c_uint64)]
+        ("store_bytes", C.c_uint64), ("file_bytes", C.c_uint64)] + [
+        (n, C.c_uint32) for n in ("gram_keys", "key_buckets", "g4_bits", "class_run", "class_and_mask",
+                                  "class_ranges")] + [("class_lo", C.c_uint32 * 2), ("class_hi", C.c_uint32 * 2)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        d = {}
+        for n, _ in self._fields_:
+            v = getattr(self, n)
+            d[n] = list(v) if hasattr(v, "__len__") else int(v)
+        return d
 
 
 # Every symbol include/olm_b200.h declares: (name, restype, argtypes)

@@ -275,6 +275,16 @@ int olm_store_inspect(const char *compiled_file, olm_store_info_t *out) {
       out->len4 = v.n4;
       out->store_bytes = v.hdr.store_bytes;
       out->file_bytes = n;
+      out->gram_keys = s.n_keys;
+      out->key_buckets = s.params.key_mask + 1;
+      out->g4_bits = s.params.g4_words * 32;
+      out->class_run = s.params.cls.run;
+      out->class_and_mask = s.params.cls.and_mask;
+      out->class_ranges = s.params.cls.n_ranges;
+      for (int i = 0; i < 2; ++i) {
+        out->class_lo[i] = s.params.cls.lo[i];
+        out->class_hi[i] = s.params.cls.hi[i];
+      }
       rc = 0;
     } else {
       std::fprintf(stderr, "libomega_match(b200): %s: %s\n", compiled_file, e2.empty() ? "self check failed" : e2.c_str());

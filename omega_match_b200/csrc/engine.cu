@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -32,6 +33,8 @@ constexpr uint64_t kWinStride = kWindowBytes + 256;    // normalised windows are
 constexpr uint64_t kNormFront = 256;                   // readable bytes in front of window 0
 constexpr uint32_t kTilesPerWindow = kWindowBytes / kTileBytes;
 constexpr uint32_t kMaxBatches = 1u << 16;
+constexpr uint64_t kSegmentBytes = uint64_t(kBatchWindows) * kWindowBytes; // host path: H2D/scan pipeline unit (256 MiB)
+constexpr uint64_t kPipelineMin = 2 * kSegmentBytes;                       // shorter haystacks: one copy, one scan
 
 #define OLM_CUDA(expr)                                                                          \
   do {                                                                                          \
@@ -79,7 +82,12 @@ int upload(DevBuf &b, const std::vector<T> &v, const T **out) {
 struct EngineImpl {
   int device = 0, sms = 0;
   size_t smem_limit = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  // host path: the haystack arrives in segments; seg_events[i] fires when bytes
+  // [0, (i+1) * seg_bytes) are in HBM (empty = everything is resident already)
+  std::vector<cudaEvent_t> seg_events;
+  uint64_t seg_bytes = 0;
+  bool streaming = false; // set by match_host around its call of match_device
   Header hdr;
   DeviceStore ds;
   ScanGeometry geo;
@@ -142,6 +150,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && upload(impl->d_set3, staged.set3, &impl->ds.set3) == 0;
   ok = ok && upload(impl->d_bitmap2, staged.bitmap2, &impl->ds.bitmap2) == 0;
   ok = ok && cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&impl->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
   ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
   impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit);
@@ -168,7 +177,9 @@ Engine::~Engine() {
     b->release();
   for (auto &ev : impl_->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto &ev : impl_->seg_events) cudaEventDestroy(ev);
   if (impl_->stream) cudaStreamDestroy(impl_->stream);
+  if (impl_->copy_stream) cudaStreamDestroy(impl_->copy_stream);
   delete impl_;
 }
 
@@ -203,7 +214,10 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   // ---- plan
   const uint64_t n_windows = windowed ? (n_own + kWindowBytes - 1) / kWindowBytes : 0;
   const uint64_t tiles = windowed ? n_windows * kTilesPerWindow : (n_own + kTileBytes - 1) / kTileBytes;
-  const uint64_t n_batches = windowed ? (n_windows + kBatchWindows - 1) / kBatchWindows : 1;
+  // plain stores: one launch, or one per segment while the host path streams the bytes in
+  const uint64_t seg = (!windowed && E.streaming && E.seg_bytes) ? E.seg_bytes : 0;
+  const uint64_t n_batches =
+      windowed ? (n_windows + kBatchWindows - 1) / kBatchWindows : (seg ? (n_own + seg - 1) / seg : 1);
   if (tiles >= 0xFFFFFFF0ull || n_batches > kMaxBatches) {
     std::fprintf(stderr, "libomega_match(b200): haystack too large for one call\n");
     return -1;
@@ -214,7 +228,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   if (E.misc.ensure(misc_total_off + 256)) return -1;
   unsigned int *d_tickets = static_cast<unsigned int *>(E.misc.p);
   unsigned int *d_redo_counts = d_tickets + kMaxBatches;
-  const uint64_t tiles_per_launch = windowed ? uint64_t(kBatchWindows) * kTilesPerWindow : tiles;
+  const uint64_t tiles_per_launch =
+      windowed ? uint64_t(kBatchWindows) * kTilesPerWindow : (seg ? (seg + kTileBytes - 1) / kTileBytes : tiles);
   if (E.redo.ensure((tiles_per_launch + 1) * 4)) return -1;
   if (E.tile_desc.ensure((tiles_per_launch + 1) * sizeof(TileDesc))) return -1;
   if (E.tile_out.ensure((tiles_per_launch + 1) * 8)) return -1;
@@ -281,19 +296,27 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
       P.buf_len = (r.slice_len + 15) & ~uint64_t(15);
       P.seg_buf_off = -(int64_t)r.slice_begin;
       P.seg_len = r.global_size;
-      P.scan_begin = r.own_begin;
-      P.scan_end = r.own_end;
-      P.num_tiles = (uint32_t)tiles;
-      P.ticket = d_tickets;
-      P.redo_count = d_redo_counts;
-      OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
-      ++scan_launches;
+      for (uint64_t b = 0; b < n_batches; ++b) {
+        P.scan_begin = r.own_begin + (seg ? b * seg : 0);
+        P.scan_end = seg ? std::min<uint64_t>(r.own_end, P.scan_begin + seg) : r.own_end;
+        P.num_tiles = (uint32_t)((P.scan_end - P.scan_begin + kTileBytes - 1) / kTileBytes);
+        P.ticket = d_tickets + b;
+        P.redo_count = d_redo_counts + b;
+        if (E.streaming) { // the scan reads a halo past its segment: wait for the next one too
+          const size_t need = std::min<size_t>(E.seg_events.size() - 1, size_t(b) + 1);
+          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[need], 0));
+        }
+        OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
+        ++scan_launches;
+      }
     } else {
       float tf_ms = 0.f;
       (void)tf_ms;
       for (uint64_t b = 0; b < n_batches; ++b) {
         const uint64_t w0 = b * kBatchWindows;
         const uint32_t nw = (uint32_t)std::min<uint64_t>(kBatchWindows, n_windows - w0);
+        if (E.streaming)
+          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[std::min<size_t>(E.seg_events.size() - 1, size_t(b))], 0));
         TransformParams T{};
         T.src = static_cast<const uint8_t *>(r.dev);
         T.src_off = (r.own_begin - r.slice_begin) + w0 * kWindowBytes;
@@ -388,9 +411,33 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   if (cudaSetDevice(E.device) != cudaSuccess) return bail();
   const size_t padded = ((n + 15) & ~size_t(15)) + 256;
   if (E.hay.ensure(padded)) return bail();
-  cudaEventRecord(E.ev[4], E.stream);
-  if (cudaMemcpyAsync(E.hay.p, haystack, n, cudaMemcpyHostToDevice, E.stream) != cudaSuccess) return bail();
-  cudaEventRecord(E.ev[5], E.stream);
+  // H2D: long haystacks arrive in 256 MiB segments on the copy stream while earlier segments
+  // are being scanned (match_device waits on the segment events); short ones in one copy.
+  const uint64_t nseg = n >= kPipelineMin ? (n + kSegmentBytes - 1) / kSegmentBytes : 1;
+  while (E.seg_events.size() < nseg) {
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail();
+    E.seg_events.push_back(ev);
+  }
+  while (E.seg_events.size() > nseg) { // match_device indexes by size: keep exactly nseg
+    cudaEventDestroy(E.seg_events.back());
+    E.seg_events.pop_back();
+  }
+  E.seg_bytes = nseg > 1 ? kSegmentBytes : 0;
+  cudaEventRecord(E.ev[4], E.copy_stream);
+  for (uint64_t i = 0; i < nseg; ++i) {
+    const uint64_t b = i * kSegmentBytes, e = nseg > 1 ? std::min<uint64_t>(n, b + kSegmentBytes) : n;
+    if (cudaMemcpyAsync(static_cast<uint8_t *>(E.hay.p) + b, haystack + b, e - b, cudaMemcpyHostToDevice,
+                        E.copy_stream) != cudaSuccess)
+      return bail();
+    cudaEventRecord(E.seg_events[i], E.copy_stream);
+  }
+  cudaEventRecord(E.ev[5], E.copy_stream);
+  struct StreamingScope { // the device-resident entry points never see segments
+    EngineImpl &E;
+    explicit StreamingScope(EngineImpl &e) : E(e) { E.streaming = true; }
+    ~StreamingScope() { E.streaming = false; }
+  } streaming_scope(E);
   ScanRange r;
   r.dev = E.hay.p;
   r.slice_begin = 0;
@@ -402,6 +449,7 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   olm_cuda_results_t dres;
   if (match_device(r, f, &dres) != 0) return bail();
   float ms = 0.f;
+  cudaStreamSynchronize(E.copy_stream);
   cudaEventElapsedTime(&ms, E.ev[4], E.ev[5]);
   E.last.h2d_ms = ms;
   if (dres.count) {

@@ -416,3 +416,105 @@ def test_large_synthetic_properties(store_cache):
         want = o.match(pre)
         got = m.match_arrays(pre)
         assert same_matches(got, want), describe_diff(got, want)
+
+
+# ---- byte-class prefilter, lean path, streaming host path ------------------------------------
+
+def _class_haystack(rng, n, alphabet, breakers, run_mean):
+    """Runs of class bytes of random length separated by single non-class bytes, so that runs
+    shorter than / equal to / longer than the prefilter's run length all occur."""
+    out = np.empty(n, dtype=np.uint8)
+    i = 0
+    while i < n:
+        r = int(rng.integers(1, 2 * run_mean))
+        r = min(r, n - i)
+        out[i:i + r] = rng.choice(alphabet, size=r)
+        i += r
+        if i < n:
+            out[i] = rng.choice(breakers)
+            i += 1
+    return out
+
+
+@pytest.mark.parametrize("kind", ["letters", "digits", "hex-two-ranges", "with-len4", "min8", "mixed-case-fold"])
+def test_class_prefilter_stores(store_cache, kind):
+    """Stores whose patterns start with bytes from a small class take the SWAR prefilter
+    (device_tables.h ByteClass): runs just below / at / above the run length, class bytes at
+    tile and chunk edges, every flag that the lean and the generic path handle."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(kind.encode()))
+    lower = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz", dtype=np.uint8)
+    upper = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZ", dtype=np.uint8)
+    digits = np.frombuffer(b"0123456789", dtype=np.uint8)
+    if kind == "letters":
+        alpha, lens = np.concatenate([lower, upper]), (6, 7, 9, 13, 24)
+    elif kind == "digits":
+        alpha, lens = digits, (5, 6, 11)
+    elif kind == "hex-two-ranges":
+        alpha, lens = np.concatenate([digits, lower[:6]]), (6, 8, 12, 17)
+    elif kind == "with-len4":
+        alpha, lens = lower, (4, 4, 5, 9)
+    elif kind == "min8":
+        alpha, lens = upper, (8, 9, 15, 30)
+    else:
+        alpha, lens = np.concatenate([lower[:13], upper[13:]]), (7, 10)
+    few = alpha[::max(1, alpha.size // 6)][:6]  # a small alphabet (spread over the class) so that matches happen
+    pats = sorted({bytes(rng.choice(few, size=int(rng.choice(lens)))) for _ in range(400)})
+    breakers = np.frombuffer(b" \n.-_@\x00\xff\x80", dtype=np.uint8)
+    hay = _class_haystack(rng, 200_000, few, breakers, run_mean=int(min(lens)))
+    # plant patterns flush against run edges, chunk (512) and tile (16384) edges
+    for k, pos in enumerate([0, 505, 512 - 3, 16384 - 5, 16384, 16384 * 3 - 1, 100_000, hay.size - 9, hay.size - 4]):
+        p = np.frombuffer(pats[k % len(pats)], dtype=np.uint8)
+        p = p[:max(0, hay.size - pos)]
+        hay[pos:pos + p.size] = p
+    path = store_cache(f"class-{kind}", b"\n".join(pats))
+    o = Oracle.from_olm(path)
+    with Matcher(path) as m:
+        for flags in ({}, {"longest_only": True}, {"no_overlap": True, "longest_only": True}, {"word_boundary": True},
+                      {"word_prefix": True}, {"line_start": True}, {"line_end": True, "word_suffix": True}):
+            check(m, o, hay, **flags)
+        check(m, o, hay[:5])
+        check(m, o, hay[:517])
+
+
+def test_lean_path_without_class_and_dense_redo(store_cache):
+    """Gram-only stores that do NOT qualify for the class prefilter (bytes >= 0x80, wide byte
+    spread) take the lean path with the bitmap probe in stage 1; a periodic haystack makes
+    every position match several patterns so that chunks overflow their staging area."""
+    rng = np.random.default_rng(11)
+    pats = {bytes(rng.integers(0, 256, size=int(n), dtype=np.uint8)).replace(b"\n", b"\x01") for n in rng.integers(5, 40, size=300)}
+    unit = b"\xc3\xa9t\xc3\xa9 "
+    pats |= {(unit * 8)[i:i + n] for i in range(len(unit)) for n in (5, 6, 7, 12, 13, 20)}
+    pats = sorted(pats)
+    hay = np.frombuffer(unit * 20_000 + bytes(rng.integers(0, 256, size=50_000, dtype=np.uint8)) + unit * 3000, dtype=np.uint8).copy()
+    for k in range(0, 40):
+        p = np.frombuffer(pats[(7 * k) % len(pats)], dtype=np.uint8)
+        pos = 120_000 + 1000 * k
+        hay[pos:pos + p.size] = p
+    path = store_cache("lean-dense", b"\n".join(pats))
+    o = Oracle.from_olm(path)
+    with Matcher(path) as m:
+        for flags in ({}, {"longest_only": True}, {"no_overlap": True}, {"word_boundary": True}):
+            check(m, o, hay, **flags)
+
+
+def test_streaming_host_path_matches_device_path(store_cache):
+    """Host buffers of 512 MiB and more are copied in 256 MiB segments that overlap with the
+    scan (engine.cu match_host).  The record stream must equal the one of the device-resident
+    call on the same bytes, for a plain and for a transforming store."""
+    torch = pytest.importorskip("torch")
+    import synth_torch
+    n = (512 << 20) + 12345
+    pats = inputs.synth_long_patterns(20_000) + [b"zq", b"The", b"of"]
+    for sf in ((0, 0, 0), (1, 0, 1)):
+        path = store_cache(f"stream-{sf}", b"\n".join(pats), sf)
+        hay = synth_torch.synth_haystack_torch(n + 64, inputs.SEED_H5, device="cuda")
+        pb, pl = synth_torch.pack_patterns(pats[:20_000], "cuda")
+        synth_torch.plant_torch(hay[:n & ~4095], pb, pl, 99)
+        host = hay[:n].cpu().numpy()
+        with Matcher(path) as m:
+            cnt, ptr = m.match_device(hay.data_ptr(), n, longest_only=True)
+            dev = _as_matches(_device_records(torch, ptr, cnt)).copy()
+            got = m.match_arrays(host, longest_only=True)
+            assert same_matches(got, dev), describe_diff(got, dev)
+            assert cnt > 100_000

@@ -184,3 +184,32 @@ def test_torch_generators_equal_numpy():
     t = torch.from_numpy(b.copy())
     synth_torch.plant_torch(t, pb, pl, 0x99, start=8000)
     assert (a2 == t.numpy()).all()
+
+
+def test_staging_facts_and_class_prefilter_choice(tmp_path, product_lib):
+    """What store.cpp derives for the GPU: key table at load <= 0.25, gram bitmap, and the
+    byte-class prefilter only where it is sound (no 1..3 byte patterns, 7-bit leading bytes,
+    a class that excludes most byte values)."""
+    def inspect(buf, flags=(0, 0, 0)):
+        p = tmp_path / f"c{abs(hash(buf)) % 10**9}.olm"
+        Compiler.compile_from_buffer(str(p), buf, *map(bool, flags))
+        info = StoreInfoC()
+        assert product_lib.olm_store_inspect(os.fsencode(p), C.byref(info)) == 0
+        return info.as_dict()
+
+    i = inspect(b"\n".join(inputs.synth_long_patterns(5000)))  # a-zA-Z, length 6..24
+    assert (i["class_run"], i["class_and_mask"], i["class_ranges"]) == (6, 0x5F, 1)
+    assert (i["class_lo"][0], i["class_hi"][0]) == (0x41, 0x5A)
+    assert i["gram_keys"] <= i["key_buckets"] < 2 * max(8, i["gram_keys"]) and i["g4_bits"] >= 16 * i["gram_keys"]
+    i = inspect(b"0123456\n9876543210\n55555\n")  # digits, shortest 5
+    assert (i["class_run"], i["class_and_mask"], i["class_ranges"], i["class_lo"][0], i["class_hi"][0]) == (5, 0x7F, 1, 0x30, 0x39)
+    i = inspect(b"deadbeef01\ncafe0123\n")  # two ranges: 0-9, a-f
+    assert (i["class_run"], i["class_ranges"]) == (8, 2) and i["class_lo"] == [0x30, 0x61] and i["class_hi"] == [0x33, 0x66]
+    i = inspect(b"abcd\nabcdefgh\n")  # a 4-byte pattern limits the run to 4
+    assert i["class_run"] == 4 and i["len4"] == 1
+    assert inspect(b"abcdefgh\nxy\n")["class_run"] == 0          # short patterns: no prefilter
+    assert inspect(b"caf\xc3\xa9 au lait\nabcdefgh\n")["class_run"] == 0  # bytes >= 0x80
+    wide = b"\n".join(bytes([c]) * 8 for c in range(1, 127) if c != 10)
+    assert inspect(wide)["class_run"] == 0  # class too wide to be worth its instructions
+    i = inspect(inputs.golden_data("names.txt"))
+    assert i["class_run"] == 0 and i["len3"] == 612
