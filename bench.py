@@ -51,6 +51,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there)
+# must not get in between: fd 1 is pointed at stderr for the whole run and the line is
+# written to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -208,7 +219,7 @@ def run_reference(args):
                              "sample": f"first {n} bytes of the haystack, {cnt} matches"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_bytes=None, note=None):
@@ -412,7 +423,7 @@ def run_ours(args):
             os.unlink(tmpname)
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
