@@ -52,6 +52,9 @@ namespace olm {
 namespace {
 
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+#ifndef OLM_FAST_UNROLL
+#define OLM_FAST_UNROLL 2
+#endif
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 constexpr unsigned long long kTempBlock = 4096; // entries of temp[] a CTA reserves at a time
 
@@ -667,12 +670,13 @@ struct Scanner {
     const uint4 *keys = P.st.keys;
     const uint32_t rem_c = T.rem0 - cbase; // >= 1
     uint32_t found = 0, q2n = 0;
-    for (uint32_t base = 0; base < total; base += 64) {
-      uint32_t e[2], gram[2], bucket[2];
-      bool pass[2];
-      uint4 kb[2];
+    constexpr int U = OLM_FAST_UNROLL;
+    for (uint32_t base = 0; base < total; base += 32 * U) {
+      uint32_t e[U], gram[U], bucket[U];
+      bool pass[U];
+      uint4 kb[U];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         const uint32_t idx = base + u * 32 + lane;
         pass[u] = idx < total;
         e[u] = pass[u] ? *reinterpret_cast<const uint16_t *>(smem_base + q1_off + 2u * idx) : 0u;
@@ -692,8 +696,8 @@ struct Scanner {
         if (pass[u]) kb[u] = __ldg(keys + bucket[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && base + 32 >= total) break;
+      for (int u = 0; u < U; ++u) {
+        if (u > 0 && base + u * 32 >= total) break;
         const uint32_t g = gram[u];
         bool hit = pass[u] && (kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g);
         // rare: the home bucket is full and does not hold the gram -> next bucket(s)
