@@ -601,14 +601,15 @@ struct Scanner {
   //   sb_off/g4_off/q1_off/q2_off: byte offsets into the CTA's dynamic shared memory.
   template <int MODE>
   __device__ __forceinline__ uint32_t scan_chunk_fast(const TileCtx &T, uint8_t *smem_base, uint32_t sb_off,
-                                                      uint32_t g4_off, uint32_t q1_off, uint32_t q2_off,
-                                                      uint32_t cbase, uint32_t lane, uint32_t *stage, uint32_t cap,
-                                                      unsigned long long out_base, unsigned long long emit_base,
-                                                      const uint32_t *map, uint32_t *overflow) const {
+                                                      uint32_t g4_off, uint32_t p23_off, uint32_t q1_off,
+                                                      uint32_t q2_off, uint32_t cbase, uint32_t lane, uint32_t *stage,
+                                                      uint32_t cap, unsigned long long out_base,
+                                                      unsigned long long emit_base, const uint32_t *map,
+                                                      uint32_t *overflow) const {
     const uint32_t lpos = cbase + lane * 16;
     const uint32_t src = sb_off + kTilePre + lpos;
     const uint4 v = *reinterpret_cast<const uint4 *>(smem_base + src);
-    uint32_t cand = 0;
+    uint32_t cand = 0, cp = 0; // cp: candidates of the 1..3 byte patterns (HAS_P23)
     if (HAS_CLS) {
       const uint2 nx = *reinterpret_cast<const uint2 *>(smem_base + src + 16);
       uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
@@ -625,14 +626,24 @@ struct Scanner {
       const uint32_t w4 = *reinterpret_cast<const uint32_t *>(smem_base + src + 16);
       const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
       const uint32_t sh = P.st.g4_shift;
+      const uint32_t pand = P.st.p23_and, pmul = P.st.p23_mul, psh = P.st.p23_shift;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
-        const uint32_t b = (gram * kHashMul) >> sh;
-        const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + g4_off + ((b >> 5) << 2));
-        cand |= ((word >> (b & 31)) & 1u) << k;
+        if (HAS_G4) {
+          const uint32_t b = (gram * kHashMul) >> sh;
+          const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + g4_off + ((b >> 5) << 2));
+          cand |= ((word >> (b & 31)) & 1u) << k;
+        }
+        if (HAS_P23) {
+          const uint32_t b = ((gram & pand) * pmul) >> psh;
+          const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + p23_off + ((b >> 5) << 2));
+          cp |= ((word >> (b & 31)) & 1u) << k;
+        }
       }
     }
+    const uint32_t cg = cand; // gram candidates
+    cand |= cp;
     if (lpos + 16 > T.nscan) cand &= lpos >= T.nscan ? 0u : ((1u << (T.nscan - lpos)) - 1u);
     const uint32_t cnt = __popc(cand);
     uint32_t incl = cnt;
@@ -649,14 +660,19 @@ struct Scanner {
         const uint32_t eb = lane * 16;
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-          if ((cand >> k) & 1u) {
-            *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)(eb + k);
+          if ((cand >> k) & 1u) { // entry: position | gram candidate << 9 | short candidate << 10
+            uint32_t ent = eb + k;
+            if (HAS_P23) ent |= (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10);
+            *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)ent;
             qa += 2;
           }
       } else {
-        const uint32_t eb = lane * 16 - 1; // __ffs is 1-based
+        const uint32_t eb = lane * 16;
         while (cand) {
-          *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)(eb + __ffs(cand));
+          const uint32_t k = __ffs(cand) - 1;
+          uint32_t ent = eb + k;
+          if (HAS_P23) ent |= (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10);
+          *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)ent;
           cand &= cand - 1;
           qa += 2;
         }
@@ -673,13 +689,19 @@ struct Scanner {
     constexpr int U = OLM_FAST_UNROLL;
     for (uint32_t base = 0; base < total; base += 32 * U) {
       uint32_t e[U], gram[U], bucket[U];
-      bool pass[U];
+      bool pass[U], shortc[U];
       uint4 kb[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t idx = base + u * 32 + lane;
         pass[u] = idx < total;
         e[u] = pass[u] ? *reinterpret_cast<const uint16_t *>(smem_base + q1_off + 2u * idx) : 0u;
+        shortc[u] = false;
+        if (HAS_P23) { // unpack the flags; without a gram candidate there is no key probe
+          shortc[u] = (e[u] >> 10) & 1u;
+          pass[u] = pass[u] && ((e[u] >> 9) & 1u);
+          e[u] &= 511u;
+        }
         const uint32_t a = tile_off + e[u];
         const uint32_t lo = *reinterpret_cast<const uint32_t *>(smem_base + (a & ~3u));
         const uint32_t hi = *reinterpret_cast<const uint32_t *>(smem_base + (a & ~3u) + 4);
@@ -693,26 +715,29 @@ struct Scanner {
         }
         bucket[u] = h >> key_shift;
         kb[u] = make_uint4(empty, empty, empty, empty);
-        if (pass[u]) kb[u] = __ldg(keys + bucket[u]);
+        if (HAS_G4 && pass[u]) kb[u] = __ldg(keys + bucket[u]);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (u > 0 && base + u * 32 >= total) break;
         const uint32_t g = gram[u];
-        bool hit = pass[u] && (kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g);
+        bool hit = HAS_G4 && pass[u] && (kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g);
         // rare: the home bucket is full and does not hold the gram -> next bucket(s)
-        if (__any_sync(kFull, pass[u] && !hit && kb[u].w != empty)) {
+        if (HAS_G4 && __any_sync(kFull, pass[u] && !hit && kb[u].w != empty)) {
           while (pass[u] && !hit && kb[u].w != empty) {
             bucket[u] = (bucket[u] + 1) & P.st.key_mask;
             kb[u] = __ldg(keys + bucket[u]);
             hit = kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g;
           }
         }
-        const uint32_t bal = __ballot_sync(kFull, hit);
+        const bool want = hit || (HAS_P23 && shortc[u]);
+        const uint32_t bal = __ballot_sync(kFull, want);
         if (!bal) continue;
-        if (hit) {
-          const uint32_t place = kb[u].x == g ? 0u : kb[u].y == g ? 1u : kb[u].z == g ? 2u : 3u;
-          q2[q2n + __popc(bal & lt)] = ((unsigned long long)(cbase + e[u]) << 32) | (4u * bucket[u] + place);
+        if (want) {
+          uint32_t slot = kNoSlot;
+          if (hit) slot = 4u * bucket[u] + (kb[u].x == g ? 0u : kb[u].y == g ? 1u : kb[u].z == g ? 2u : 3u);
+          q2[q2n + __popc(bal & lt)] =
+              ((unsigned long long)((cbase + e[u]) | (HAS_P23 && shortc[u] ? 0x10000u : 0u)) << 32) | slot;
         }
         q2n += __popc(bal);
         __syncwarp();
@@ -999,6 +1024,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
   unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
   const uint32_t ring_off = (uint32_t)(L.ring - smem), g4_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
+  const uint32_t p23_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.p23s) - smem);
   const uint32_t q1_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q1) - smem);
   const uint32_t q2_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q2) - smem);
   for (;;) {
@@ -1033,8 +1059,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     uint32_t n = 0;
     if (cbase < T.nscan) {
       if (FAST)
-        n = sc.template scan_chunk_fast<kStageMode>(T, smem, ring_off + s * kStageBytes, g4_off, q1_off, q2_off, cbase,
-                                                    lane, stage, cap, 0, 0, nullptr, &H.ovf[b]);
+        n = sc.template scan_chunk_fast<kStageMode>(T, smem, ring_off + s * kStageBytes, g4_off, p23_off, q1_off, q2_off,
+                                                    cbase, lane, stage, cap, 0, 0, nullptr, &H.ovf[b]);
       else
         n = sc.template scan_chunk<kStageMode>(T, cbase, lane, stage, cap, my_q1, my_q2, 0, 0, nullptr, &H.ovf[b]);
     }
@@ -1183,8 +1209,8 @@ __global__ void __launch_bounds__(kPlaceThreads) place_kernel(const __grid_const
 template <bool G, bool Q, bool C>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
   const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
-  // the lean per-candidate path covers: gram patterns only, no position predicate requested
-  constexpr bool can_fast = G && !Q;
+  // the lean per-candidate path covers every store, as long as no position predicate is requested
+  constexpr bool can_fast = G || Q;
   const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
   if (fast)
     scan_kernel<G, Q, C, can_fast><<<grid, kScanThreads, smem, stream>>>(p);
@@ -1205,8 +1231,8 @@ template <bool G, bool Q, bool C>
 cudaError_t configure_variant(size_t smem_limit) {
   cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
   if (e != cudaSuccess) return e;
-  if (G && !Q) {
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G && !Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  if (G || Q) {
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     if (e != cudaSuccess) return e;
   }
   return cudaFuncSetAttribute(redo_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
