@@ -93,7 +93,7 @@ struct EngineImpl {
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, tile_desc, tile_out, temp, redo, misc, norm, map, windows, ghost, fscratch;
+  DevBuf hay, out, out2, chunk_desc, span_base, temp, misc, norm, map, windows, ghost, fscratch;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -172,7 +172,7 @@ Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
-                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->tile_desc, &impl_->tile_out, &impl_->temp, &impl_->redo, &impl_->misc,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->misc,
                     &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch})
     b->release();
   for (auto &ev : impl_->ev)
@@ -227,12 +227,12 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   const size_t misc_total_off = size_t(kMaxBatches) * 8;
   if (E.misc.ensure(misc_total_off + 256)) return -1;
   unsigned int *d_tickets = static_cast<unsigned int *>(E.misc.p);
-  unsigned int *d_redo_counts = d_tickets + kMaxBatches;
+  unsigned int *d_redo_flags = d_tickets + kMaxBatches;
   const uint64_t tiles_per_launch =
       windowed ? uint64_t(kBatchWindows) * kTilesPerWindow : (seg ? (seg + kTileBytes - 1) / kTileBytes : tiles);
-  if (E.redo.ensure((tiles_per_launch + 1) * 4)) return -1;
-  if (E.tile_desc.ensure((tiles_per_launch + 1) * sizeof(TileDesc))) return -1;
-  if (E.tile_out.ensure((tiles_per_launch + 1) * 8)) return -1;
+  const uint64_t chunks_per_launch = tiles_per_launch * kTileChunks;
+  if (E.chunk_desc.ensure((chunks_per_launch + 1) * sizeof(ChunkDesc))) return -1;
+  if (E.span_base.ensure((chunks_per_launch / kPrefixSpan + 2) * 8)) return -1;
   unsigned long long *d_total = reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + misc_total_off);
   unsigned long long *d_ftotal = d_total + 1;
   unsigned long long *d_counters = d_total + 2;
@@ -264,18 +264,22 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   for (int attempt = 0; attempt < 4; ++attempt) {
     if (E.out.ensure(cap * sizeof(Record))) return -1;
     cap = E.out.cap / sizeof(Record);
-    const uint64_t temp_cap = cap + cap / 2 + kTempSlackPerSm * uint64_t(E.sms) * n_batches + temp_extra;
+    const uint64_t temp_cap = cap + cap / 2 + temp_slack_entries(E.sms) * n_batches + temp_extra;
+    if (temp_cap > 0xFFFFFFF0ull) { // chunk descriptors index temp[] with 32 bits
+      std::fprintf(stderr, "libomega_match(b200): too many matches for one call\n");
+      return -1;
+    }
     if (E.temp.ensure(temp_cap * 4)) return -1;
     OLM_CUDA(cudaMemsetAsync(d_tickets, 0, n_batches * 4, E.stream));
-    OLM_CUDA(cudaMemsetAsync(d_redo_counts, 0, n_batches * 4, E.stream));
+    OLM_CUDA(cudaMemsetAsync(d_redo_flags, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_total, 0, 128, E.stream));
     uint32_t launches = 0, scan_launches = 0;
     OLM_CUDA(cudaEventRecord(E.ev[0], E.stream));
 
     ScanParams P{};
     P.st = E.ds;
-    P.tile_desc = static_cast<TileDesc *>(E.tile_desc.p);
-    P.out_base = static_cast<unsigned long long *>(E.tile_out.p);
+    P.chunk_desc = static_cast<ChunkDesc *>(E.chunk_desc.p);
+    P.span_base = static_cast<unsigned long long *>(E.span_base.p);
     P.temp = static_cast<uint32_t *>(E.temp.p);
     P.temp_cap = temp_cap;
     P.temp_count = d_temp_count;
@@ -286,10 +290,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.counters = d_counters;
     P.flags = fl;
     P.stages = E.geo.stages;
-    P.sets = E.geo.sets;
     P.chunk_cap = E.geo.chunk_cap;
     P.tail_byte = 0;
-    P.redo_list = static_cast<uint32_t *>(E.redo.p);
 
     if (!windowed) {
       P.buf = static_cast<const uint8_t *>(r.dev);
@@ -301,7 +303,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.scan_end = seg ? std::min<uint64_t>(r.own_end, P.scan_begin + seg) : r.own_end;
         P.num_tiles = (uint32_t)((P.scan_end - P.scan_begin + kTileBytes - 1) / kTileBytes);
         P.ticket = d_tickets + b;
-        P.redo_count = d_redo_counts + b;
+        P.redo_flag = d_redo_flags + b;
         if (E.streaming) { // the scan reads a halo past its segment: wait for the next one too
           const size_t need = std::min<size_t>(E.seg_events.size() - 1, size_t(b) + 1);
           OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[need], 0));
@@ -340,7 +342,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.tiles_per_win = kTilesPerWindow;
         P.num_tiles = nw * kTilesPerWindow;
         P.ticket = d_tickets + b;
-        P.redo_count = d_redo_counts + b;
+        P.redo_flag = d_redo_flags + b;
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
         ++scan_launches;
       }

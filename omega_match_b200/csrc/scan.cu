@@ -7,8 +7,7 @@
 // concatenate + radix sort of finalize_match_results (matcher.c:587-623, :258-325).
 //
 // Shape of scan_kernel
-//   * persistent CTAs (grid = #SMs) of 32 warps: 30 scanning warps, one finisher warp, one
-//     producer warp.  Tiles of 16 KiB positions are handed out by an atomic ticket, so tile k
+//   * persistent CTAs (grid = #SMs) of 32 warps: 31 scanning warps and one producer warp.  Tiles of 16 KiB positions are handed out by an atomic ticket, so tile k
 //     is always started before k+1; inside a CTA the 32 chunks (512 positions) of a tile are
 //     grabbed dynamically by the scanning warps -- no warp waits for a slower one;
 //   * producer: each tile (+16 bytes in front, +112 behind) is brought into shared memory by
@@ -29,17 +28,17 @@
 //     length), remaining bytes against the pattern store, end predicates, the 4/3/2/1-byte
 //     sets; accepted matches are appended in candidate order (ballot + popc) to the chunk's
 //     staging area;
-//   * finisher: chunk totals of tile k -> exclusive prefixes (one chunk per lane), ONE global
-//     atomic reserves the tile's run in temp[], the staged matches go there as packed 4-byte
-//     entries (position order) and the tile descriptor {count, temp_base} is written.  No CTA
-//     ever waits for another CTA.  Staging sets rotate, so scanning runs ahead of the finisher;
-//   * prefix_kernel: exclusive prefix over the tile counts = every tile's first index in the
-//     result array;  place_kernel: expands the packed entries into final 24-byte records at
-//     those indices (offset ascending, length descending: the order radix_sort_matches
+//   * hand-over: the warp that scanned a chunk takes a run of temp[] from its own block (one
+//     global atomic per 1024 entries), copies the staged matches there as packed 4-byte
+//     entries (position order) and writes the chunk descriptor {count, temp_index}.  No warp
+//     waits for another warp, no CTA for another CTA;
+//   * prefix_sum_kernel / prefix_scan_kernel: first result index of every span of 4096 chunks;
+//     place_kernel: per-chunk prefix inside the span, packed entries -> final 24-byte records at
+//     their final index (offset ascending, length descending: the order radix_sort_matches
 //     produces, without a sort);
-//   * a tile whose matches do not fit the staging area goes on the redo list; redo_kernel
-//     (exits at once when the list is empty) re-evaluates such tiles and writes their records
-//     directly (counts are always exact, so bases do not change).
+//   * a chunk whose matches do not fit its staging area is only counted (counts are always
+//     exact); redo_kernel (exits at once when there is none) evaluates such chunks again and
+//     writes their records directly at the index place_kernel computed.
 #include "scan.cuh"
 
 #include <cstdio>
@@ -56,7 +55,6 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 #define OLM_FAST_UNROLL 2
 #endif
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-constexpr unsigned long long kTempBlock = 4096; // entries of temp[] a CTA reserves at a time
 
 struct StageInfo { // written by the producer lane, read by everyone after the mbarrier wait
   unsigned long long p0;   // segment-relative position of the tile's first byte
@@ -79,11 +77,7 @@ struct SmemHeader {
   uint64_t full[kMaxStages];
   uint64_t scanned[kMaxStages];
   uint32_t chunk_ctr; // next chunk of the CTA's tile sequence
-  uint32_t drained;   // tiles whose staged matches have been copied out (finisher)
   uint32_t end_k;     // first tile iteration without a tile (kNoTile until the tickets run out)
-  uint32_t ovf[kMaxSets];
-  uint32_t done[kInfoRing]; // chunks of tile iteration k (entry k % kInfoRing) that have been scanned
-  uint32_t ccnt[kMaxSets][kTileChunks];
   StageInfo info[kInfoRing];
 };
 static_assert(sizeof(SmemHeader) <= kSmemHeader, "header does not fit");
@@ -883,12 +877,11 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
 template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t S = P.stages, NB = P.sets, cap = P.chunk_cap;
-  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, NB * kTileChunks * cap);
+  const uint32_t S = P.stages, cap = P.chunk_cap;
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, kScanWarps * cap);
   SmemHeader &H = *L.H;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t fl = P.flags;
 
   load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
   if (tid == 0) {
@@ -897,22 +890,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       mbar_init(&H.scanned[s], kTileChunks);
     }
     H.chunk_ctr = 0;
-    H.drained = 0;
     H.end_k = kNoTile;
-    for (uint32_t b = 0; b < kMaxSets; ++b) H.ovf[b] = 0;
-    for (uint32_t i = 0; i < kInfoRing; ++i) {
-      H.info[i].seq = kNoTile;
-      H.done[i] = 0;
-    }
+    for (uint32_t i = 0; i < kInfoRing; ++i) H.info[i].seq = kNoTile;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == kScanWarps + 1) {
+  if (warp == kScanWarps) {
     // ============================ producer warp (one lane) ============================
     if (lane != 0) return;
-    // Tile iteration k of this CTA -> stage k % S.  The info entry is published with a fence +
-    // volatile `seq` store: readers that do not wait on `full` (the finisher) spin on seq.
+    // Tile iteration k of this CTA -> stage k % S.  `seq` is stored first so that a scanning
+    // warp can tell that the stage's mbarrier is in ITS generation before it waits on it.
     auto produce = [&](uint32_t k) {
       const uint32_t s = k % S;
       const uint32_t t = atomicAdd(P.ticket, 1u);
@@ -938,82 +926,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     for (uint32_t k = 0;; ++k) {
       if (H.info[k % kInfoRing].tile == kNoTile) break;
       mbar_wait(&H.scanned[s], ph);
-      produce(k + D); // stage (k + D) % S last held tile k + D - S <= k: free
+      produce(k + D); // stage (k + D) % S last held tile k + D - S <= k: free; so is the info entry
       if (++s == S) {
         s = 0;
         ph ^= 1;
-      }
-    }
-    return;
-  }
-
-  if (warp == kScanWarps) {
-    // ============ finisher warp: tile descriptor + staged matches -> temp[] ============
-    unsigned long long blk_next = 0, blk_left = 0; // lane 0: this CTA's current block of temp[]
-    for (uint32_t k = 0;; ++k) {
-      const StageInfo &I = H.info[k % kInfoRing];
-      // (no wait on `full` here: the finisher may lag the producer by more than one
-      // generation of the stage, and an mbarrier only tells two phases apart)
-      while (ld_volatile_shared(&I.seq) != k) __nanosleep(32);
-      __threadfence_block();
-      const uint32_t tile = I.tile;
-      if (tile == kNoTile) break;
-      // all chunks scanned?  (a counter, not the `scanned` mbarrier: with more staging sets
-      // than ring stages the finisher may be several generations of the stage behind)
-      while (ld_volatile_shared(&H.done[k % kInfoRing]) != (uint32_t)kTileChunks) __nanosleep(32);
-      __threadfence_block();
-      const uint32_t b = k % NB;
-      // chunk totals -> exclusive prefixes (lane = chunk)
-      const uint32_t c = lane < (uint32_t)kTileChunks ? H.ccnt[b][lane] : 0u;
-      uint32_t incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, incl, d);
-        if (lane >= (uint32_t)d) incl += t;
-      }
-      const uint32_t cpre = incl - c;
-      const uint32_t tile_total = __shfl_sync(kFull, incl, 31);
-      const uint32_t ovf = H.ovf[b];
-      unsigned long long base = 0;
-      if (lane == 0) {
-        if (tile_total && !ovf) {
-          // temp[] is handed out in blocks of kTempBlock entries (one global atomic per block,
-          // not per tile); a tile's run never straddles blocks
-          if (tile_total > blk_left) {
-            const unsigned long long want = 4ull * tile_total > kTempBlock ? 4ull * tile_total : kTempBlock;
-            blk_next = atomicAdd(P.temp_count, want);
-            blk_left = want;
-          }
-          base = blk_next;
-          blk_next += tile_total;
-          blk_left -= tile_total;
-        }
-        TileDesc d;
-        d.count = tile_total;
-        d.overflow = ovf;
-        d.temp_base = base;
-        *reinterpret_cast<uint4 *>(P.tile_desc + tile) = *reinterpret_cast<const uint4 *>(&d);
-        if (ovf) P.redo_list[atomicAdd(P.redo_count, 1u)] = tile;
-      }
-      base = __shfl_sync(kFull, base, 0);
-      // (when temp[] is too small the entries are dropped; the host sees total > capacity and
-      // repeats the call with the exact size)
-      if (!ovf && tile_total && base + tile_total <= P.temp_cap) {
-        const uint32_t *set = L.staging + (size_t)b * kTileChunks * cap;
-        for (uint32_t ci = 0; ci < (uint32_t)kTileChunks; ++ci) {
-          const uint32_t n = __shfl_sync(kFull, c, ci);
-          if (n == 0) continue;
-          uint32_t *dst = P.temp + base + __shfl_sync(kFull, cpre, ci);
-          const uint32_t *st = set + (size_t)ci * cap;
-          for (uint32_t i = lane; i < n; i += 32) dst[i] = st[i];
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        H.ovf[b] = 0;
-        H.done[k % kInfoRing] = 0;
-        __threadfence_block();
-        *reinterpret_cast<volatile uint32_t *>(&H.drained) = k + 1; // the set may be staged into again
       }
     }
     return;
@@ -1023,10 +939,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
   uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
   unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
+  uint32_t *my_stage = L.staging + (size_t)warp * cap;
   const uint32_t ring_off = (uint32_t)(L.ring - smem), g4_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
   const uint32_t p23_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.p23s) - smem);
   const uint32_t q1_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q1) - smem);
   const uint32_t q2_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q2) - smem);
+  unsigned long long blk_next = 0; // this warp's block of temp[]: next free entry ...
+  uint32_t blk_left = 0;           // ... and how many are left
   for (;;) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(&H.chunk_ctr, 1u);
@@ -1046,103 +965,149 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     }
     if (over) break;
     mbar_wait(&H.full[s], gen & 1u);
-    if (I.tile == kNoTile) break;
-    const uint32_t b = k & (NB - 1); // NB is 2 or 4
-    if (k >= NB) { // the staging set must have been copied out (tile k - NB)
-      while ((int)(ld_volatile_shared(&H.drained) - (k - NB + 1)) < 0) __nanosleep(32);
-      __threadfence_block();
-    }
+    const uint32_t tile = I.tile;
+    if (tile == kNoTile) break;
     TileCtx T;
     tile_ctx(I, L.ring + (size_t)s * kStageBytes, T);
     const uint32_t cbase = ci * kChunkBytes;
-    uint32_t *stage = L.staging + ((size_t)b * kTileChunks + ci) * cap;
-    uint32_t n = 0;
+    uint32_t n = 0, ovf = 0;
     if (cbase < T.nscan) {
       if (FAST)
         n = sc.template scan_chunk_fast<kStageMode>(T, smem, ring_off + s * kStageBytes, g4_off, p23_off, q1_off, q2_off,
-                                                    cbase, lane, stage, cap, 0, 0, nullptr, &H.ovf[b]);
+                                                    cbase, lane, my_stage, cap, 0, 0, nullptr, &ovf);
       else
-        n = sc.template scan_chunk<kStageMode>(T, cbase, lane, stage, cap, my_q1, my_q2, 0, 0, nullptr, &H.ovf[b]);
+        n = sc.template scan_chunk<kStageMode>(T, cbase, lane, my_stage, cap, my_q1, my_q2, 0, 0, nullptr, &ovf);
     }
     __syncwarp();
-    if (lane == 0) {
-      H.ccnt[b][ci] = n;
-      mbar_arrive(&H.scanned[s]); // producer: the stage buffer is not read any more (release)
-      __threadfence_block();
-      atomicAdd(&H.done[k % kInfoRing], 1u); // finisher: staged matches and count are in place
+    if (lane == 0) mbar_arrive(&H.scanned[s]); // the stage buffer is not read any more
+    // ---- hand the chunk over: descriptor, and the staged matches into this warp's run of temp[]
+    ovf = __any_sync(kFull, ovf != 0);
+    ChunkDesc d;
+    d.count = n;
+    d.temp_index = 0;
+    if (ovf) {
+      d.count = n | kChunkOverflow;
+      if (lane == 0) *reinterpret_cast<volatile unsigned int *>(P.redo_flag) = 1u;
+    } else if (n) {
+      if (n > blk_left) { // a fresh block (what is left of the old one is lost)
+        const uint32_t want = n > kWarpTempBlock / 2 ? 2 * n : kWarpTempBlock;
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(P.temp_count, (unsigned long long)want);
+        blk_next = __shfl_sync(kFull, b, 0);
+        blk_left = want;
+      }
+      // (when temp[] is too small the entries are dropped; the host sees it and repeats the call)
+      if (blk_next + n <= P.temp_cap && blk_next + n <= 0xFFFFFFFFull) {
+        uint32_t *dst = P.temp + blk_next;
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = my_stage[i];
+      }
+      d.temp_index = (uint32_t)blk_next;
+      blk_next += n;
+      blk_left -= n;
     }
+    if (lane == 0)
+      *reinterpret_cast<uint2 *>(P.chunk_desc + ((size_t)tile * kTileChunks + ci)) = make_uint2(d.count, d.temp_index);
+    __syncwarp(); // my_stage is rewritten by the next chunk
   }
   sc.flush_stats(lane);
 }
 
-// Tiles of the redo list, one CTA per tile at a time: count per chunk, prefix, then evaluate
-// again writing final records at the tile's base (prefix_kernel).
+// Chunks flagged kChunkOverflow (their matches did not fit the staging area): every warp takes
+// such chunks, copies the chunk (+ the bytes around it) into a small private buffer, evaluates
+// it again and writes final records at the index place_kernel left in the descriptor.
+constexpr int kRedoBuf = kTilePre + kChunkBytes + kTileHalo; // 640
 template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
 __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, 1, 0);
-  SmemHeader &H = *L.H;
-  const uint32_t n = *P.redo_count;
-  if (blockIdx.x >= n) return;
+  if (*P.redo_flag == 0) return;
+  // header | "ring": one 640-byte buffer per warp | g4 | p23 | Q2 | Q1
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, 2, 0);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t fl = P.flags;
   load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
-  if (tid == 0) {
-    mbar_init(&H.full[0], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
+  if (warp >= kScanWarps) return;
   Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
-  sc.stat_inc = 0; // the main pass has counted these tiles already
-  uint16_t *my_q1 = L.q1 + (warp % kScanWarps) * kChunkBytes;
-  unsigned long long *my_q2 = L.q2 + (warp % kScanWarps) * kQ2Entries;
+  sc.stat_inc = 0; // the main pass has counted these chunks already
+  uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
+  unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
+  uint8_t *buf = L.ring + (size_t)warp * kRedoBuf; // 31 * 640 < 2 * kStageBytes
   const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
-  uint32_t ph = 0;
-  for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
-    const uint32_t tile = P.redo_list[e];
-    if (tid == 0) start_tile(P, tile, H.info[0], L.ring, &H.full[0]);
-    mbar_wait(&H.full[0], ph);
-    ph ^= 1;
-    TileCtx T;
-    tile_ctx(H.info[0], L.ring, T);
-    const unsigned long long emit_base = H.info[0].emit_base;
-    const uint32_t *map = use_map ? P.map + (size_t)H.info[0].win * kWindowBytes : nullptr;
-    if (warp < kScanWarps)
-      for (uint32_t ci = warp; ci < (uint32_t)kTileChunks; ci += kScanWarps) {
-        uint32_t cnt = 0;
-        if (ci * kChunkBytes < T.nscan)
-          cnt = sc.template scan_chunk<kCountMode>(T, ci * kChunkBytes, lane, nullptr, 0, my_q1, my_q2, 0, 0, nullptr, nullptr);
-        if (lane == 0) H.ccnt[0][ci] = cnt;
+  const uint64_t n_chunks = (uint64_t)P.num_tiles * kTileChunks;
+  // a warp looks at 32 descriptors at a time and takes the flagged chunks one after the other
+  for (uint64_t c0 = ((uint64_t)blockIdx.x * kScanWarps + warp) * 32; c0 < n_chunks;
+       c0 += (uint64_t)gridDim.x * kScanWarps * 32) {
+    uint32_t flagged = 0;
+    if (c0 + lane < n_chunks) flagged = P.chunk_desc[c0 + lane].count & kChunkOverflow;
+    uint32_t todo = __ballot_sync(kFull, flagged != 0);
+    while (todo) {
+      const uint64_t ch = c0 + (__ffs(todo) - 1);
+      todo &= todo - 1;
+      const uint32_t tile = (uint32_t)(ch / kTileChunks), ci = (uint32_t)(ch % kTileChunks);
+      StageInfo I;
+      fill_tile(P, tile, I);
+      const uint32_t cbase = ci * kChunkBytes;
+      // the chunk as a tile of its own: position 0 = the chunk's first byte
+      TileCtx T;
+      T.sb = buf;
+      T.p0 = I.p0 + cbase;
+      T.boff = I.boff + cbase;
+      T.rem0 = I.rem0 - cbase;
+      T.nscan = I.nscan - cbase < (uint32_t)kChunkBytes ? I.nscan - cbase : (uint32_t)kChunkBytes;
+      T.staged = I.staged - cbase < (uint32_t)(kChunkBytes + kTileHalo) ? I.staged - cbase : (uint32_t)(kChunkBytes + kTileHalo);
+      T.tail = I.tail;
+      T.first = T.p0 == 0;
+      for (uint32_t i = lane; i < T.staged + kTilePre; i += 32) {
+        const long long src = T.boff - kTilePre + (long long)i;
+        buf[i] = src >= 0 ? P.buf[src] : 0;
       }
-    __syncthreads();
-    if (warp < kScanWarps) {
-      const unsigned long long tile_base = P.out_base[tile];
-      for (uint32_t ci = warp; ci < (uint32_t)kTileChunks; ci += kScanWarps) {
-        if (ci * kChunkBytes >= T.nscan) break;
-        unsigned long long base = tile_base;
-        for (uint32_t j = 0; j < ci; ++j) base += H.ccnt[0][j];
-        sc.template scan_chunk<kDirectMode>(T, ci * kChunkBytes, lane, nullptr, 0, my_q1, my_q2, base, emit_base, map, nullptr);
+      __syncwarp();
+      // first result index: the span's base + the chunks before this one in the span
+      unsigned long long base = P.span_base[ch / kPrefixSpan];
+      {
+        const uint64_t s0 = ch - ch % kPrefixSpan;
+        unsigned long long part = 0;
+        for (uint64_t j = s0 + lane; j < ch; j += 32) part += P.chunk_desc[j].count & ~kChunkOverflow;
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) part += __shfl_xor_sync(kFull, part, dd);
+        base += part;
       }
+      const uint32_t *map = use_map ? P.map + (size_t)I.win * kWindowBytes : nullptr;
+      sc.template scan_chunk<kDirectMode>(T, 0, lane, nullptr, 0, my_q1, my_q2, base, I.emit_base, map, nullptr);
+      __syncwarp();
     }
-    __syncthreads(); // the stage buffer and ccnt are reused by the next entry
   }
 }
 
-// Exclusive prefix over the tile counts of a launch, continuing from *P.total (matches of
-// earlier launches of the same call); one CTA, 4 tiles per thread and step.
-constexpr int kPrefixThreads = 1024;
-__global__ void __launch_bounds__(kPrefixThreads, 1) prefix_kernel(const __grid_constant__ ScanParams P) {
+// ---- prefix over the chunk counts of a launch -------------------------------------------------
+// span_base[b] <- matches in span b (kPrefixSpan chunks)
+constexpr int kPrefixThreads = 256;
+__global__ void __launch_bounds__(kPrefixThreads) prefix_sum_kernel(const __grid_constant__ ScanParams P) {
   __shared__ unsigned long long s_warp[kPrefixThreads / 32];
+  const uint64_t n_chunks = (uint64_t)P.num_tiles * kTileChunks;
+  const uint64_t c0 = (uint64_t)blockIdx.x * kPrefixSpan;
+  unsigned long long sum = 0;
+  for (uint32_t i = threadIdx.x; i < kPrefixSpan; i += kPrefixThreads)
+    if (c0 + i < n_chunks) sum += P.chunk_desc[c0 + i].count & ~kChunkOverflow;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kPrefixThreads / 32; ++w) t += s_warp[w];
+    P.span_base[blockIdx.x] = t;
+  }
+}
+// span_base[b] <- *P.total + sum of the spans before b; *P.total += everything (one CTA)
+__global__ void __launch_bounds__(1024, 1) prefix_scan_kernel(const __grid_constant__ ScanParams P, uint32_t n_spans) {
+  __shared__ unsigned long long s_warp[32];
   __shared__ unsigned long long s_carry;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_carry = *P.total;
   __syncthreads();
-  for (uint32_t t0 = 0; t0 < P.num_tiles; t0 += kPrefixThreads * 4) {
-    const uint32_t first = t0 + tid * 4;
-    uint32_t c[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = first + i < P.num_tiles ? P.tile_desc[first + i].count : 0u;
-    const unsigned long long mine = (unsigned long long)c[0] + c[1] + c[2] + c[3];
+  for (uint32_t b0 = 0; b0 < n_spans; b0 += 1024) {
+    const unsigned long long mine = b0 + tid < n_spans ? P.span_base[b0 + tid] : 0ull;
     unsigned long long incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1153,48 +1118,65 @@ __global__ void __launch_bounds__(kPrefixThreads, 1) prefix_kernel(const __grid_
     __syncthreads();
     unsigned long long before = s_carry;
     for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
-    unsigned long long run = before + incl - mine;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (first + i < P.num_tiles) P.out_base[first + i] = run;
-      run += c[i];
-    }
+    if (b0 + tid < n_spans) P.span_base[b0 + tid] = before + incl - mine;
     __syncthreads();
-    if (tid == kPrefixThreads - 1) s_carry = run;
+    if (tid == 1023) s_carry = before + incl;
     __syncthreads();
   }
   if (tid == 0) *P.total = s_carry;
 }
 
-// Packed entries of temp[] -> final records.  A warp takes 32 tiles at a time (coalesced
-// descriptor reads) and copies the tiles that have matches one after the other.
-constexpr int kPlaceThreads = 256;
-__global__ void __launch_bounds__(kPlaceThreads) place_kernel(const __grid_constant__ ScanParams P) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps = gridDim.x * (kPlaceThreads / 32);
-  const uint32_t gw = blockIdx.x * (kPlaceThreads / 32) + (threadIdx.x >> 5);
+// Packed entries of temp[] -> final records.  One CTA per span of kPrefixSpan chunks: exclusive
+// prefix of the counts inside the span (16 chunks per thread), then the warps copy the chunks
+// that have matches, 32 chunks per warp at a time.
+__global__ void __launch_bounds__(kPrefixThreads) place_kernel(const __grid_constant__ ScanParams P) {
+  __shared__ unsigned long long s_warp[kPrefixThreads / 32];
+  __shared__ uint32_t s_pre[kPrefixSpan]; // exclusive prefix inside the span
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t n_chunks = (uint64_t)P.num_tiles * kTileChunks;
+  const uint64_t c0 = (uint64_t)blockIdx.x * kPrefixSpan;
+  constexpr uint32_t kPer = kPrefixSpan / kPrefixThreads; // 16 consecutive chunks per thread
+  uint32_t cnt[kPer];
+  uint32_t mine = 0;
+#pragma unroll
+  for (uint32_t i = 0; i < kPer; ++i) {
+    const uint64_t ch = c0 + (uint64_t)tid * kPer + i;
+    cnt[i] = ch < n_chunks ? (P.chunk_desc[ch].count & ~kChunkOverflow) : 0u;
+    mine += cnt[i];
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, incl, d);
+    if (lane >= (uint32_t)d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t run = incl - mine;
+  for (uint32_t w = 0; w < warp; ++w) run += (uint32_t)s_warp[w];
+#pragma unroll
+  for (uint32_t i = 0; i < kPer; ++i) {
+    s_pre[tid * kPer + i] = run;
+    run += cnt[i];
+  }
+  __syncthreads();
+  const unsigned long long span0 = P.span_base[blockIdx.x];
   const bool use_map = (P.flags & kWindowMode) && !(P.flags & kIdentityMap);
-  for (uint32_t t0 = gw * 32; t0 < P.num_tiles; t0 += warps * 32) {
-    const uint32_t t = t0 + lane;
-    TileDesc d;
-    d.count = 0;
-    d.overflow = 0;
-    d.temp_base = 0;
-    unsigned long long ob = 0;
-    if (t < P.num_tiles) {
-      *reinterpret_cast<uint4 *>(&d) = __ldg(reinterpret_cast<const uint4 *>(P.tile_desc + t));
-      ob = P.out_base[t];
-    }
-    uint32_t todo = __ballot_sync(kFull, d.count != 0 && d.overflow == 0);
+  for (uint32_t g0 = warp * 32; g0 < kPrefixSpan; g0 += (kPrefixThreads / 32) * 32) {
+    const uint64_t ch = c0 + g0 + lane;
+    uint2 d = make_uint2(0, 0);
+    if (ch < n_chunks) d = *reinterpret_cast<const uint2 *>(P.chunk_desc + ch);
+    uint32_t todo = __ballot_sync(kFull, d.x != 0 && !(d.x & kChunkOverflow));
     while (todo) {
       const uint32_t src = __ffs(todo) - 1;
       todo &= todo - 1;
-      const uint32_t n = __shfl_sync(kFull, d.count, src);
-      const unsigned long long tb = __shfl_sync(kFull, d.temp_base, src);
-      const unsigned long long base = __shfl_sync(kFull, ob, src);
+      const uint32_t n = __shfl_sync(kFull, d.x, src);
+      const unsigned long long tb = __shfl_sync(kFull, d.y, src);
       if (tb + n > P.temp_cap) continue; // dropped entries: the call is repeated with a larger buffer
+      const uint64_t chs = c0 + g0 + src;
+      const unsigned long long base = span0 + s_pre[g0 + src];
       StageInfo I;
-      fill_tile(P, t0 + src, I);
+      fill_tile(P, (uint32_t)(chs / kTileChunks), I);
       const uint32_t *map = use_map ? P.map + (size_t)I.win * kWindowBytes : nullptr;
       for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t e = __ldg(P.temp + tb + i);
@@ -1218,12 +1200,15 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
     scan_kernel<G, Q, C, false><<<grid, kScanThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  prefix_kernel<<<1, kPrefixThreads, 0, stream>>>(p);
+  const uint64_t n_chunks = (uint64_t)p.num_tiles * kTileChunks;
+  const uint32_t n_spans = (uint32_t)((n_chunks + kPrefixSpan - 1) / kPrefixSpan);
+  prefix_sum_kernel<<<n_spans, kPrefixThreads, 0, stream>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  const uint32_t place_blocks = (p.num_tiles + 32 * (kPlaceThreads / 32) - 1) / (32 * (kPlaceThreads / 32));
-  place_kernel<<<place_blocks < 4u * (uint32_t)sms ? place_blocks : 4u * (uint32_t)sms, kPlaceThreads, 0, stream>>>(p);
+  prefix_scan_kernel<<<1, 1024, 0, stream>>>(p, n_spans);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, 1, 0, 0), stream>>>(p);
+  place_kernel<<<n_spans, kPrefixThreads, 0, stream>>>(p);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, 2, 0), stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -1240,27 +1225,21 @@ cudaError_t configure_variant(size_t smem_limit) {
 
 } // namespace
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t sets, uint32_t chunk_cap) {
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap) {
   return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kQ2Bytes +
-         size_t(sets) * kTileChunks * chunk_cap * 4 + kQ1Bytes;
+         size_t(kScanWarps) * chunk_cap * 4 + kQ1Bytes;
 }
 
 ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
   ScanGeometry g;
-  // ring depth and staging sets are powers of two (indexed by mask); stages + sets <= kInfoRing
+  // the ring depth is a power of two (indexed by mask); whatever shared memory is left goes to
+  // the warps' staging areas (denser matches before a chunk has to be redone)
   for (uint32_t s = kMaxStages; s >= 2; s >>= 1) {
-    if (scan_smem_bytes(st, s, 2, kChunkCapMin) > smem_limit) continue;
-    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0, 0);
-    auto cap_for = [&](uint32_t sets) { return uint32_t(spare / (size_t(sets) * kTileChunks * 4)) & ~7u; };
-    // more sets = scanning warps run further ahead of the finisher; more capacity = denser
-    // matches before a tile has to be redone
-    uint32_t sets = 2;
-    if (cap_for(8) >= 64) sets = 8;
-    else if (cap_for(4) >= 32) sets = 4;
-    uint32_t cap = cap_for(sets);
+    if (scan_smem_bytes(st, s, kChunkCapMin) > smem_limit) continue;
+    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
+    uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
     if (cap > kChunkCapMax) cap = kChunkCapMax;
     g.stages = s;
-    g.sets = sets;
     g.chunk_cap = cap;
     return g;
   }
@@ -1277,9 +1256,9 @@ cudaError_t scan_configure(size_t smem_limit) {
 }
 
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches) {
-  const size_t smem = scan_smem_bytes(p.st, p.stages, p.sets, p.chunk_cap);
+  const size_t smem = scan_smem_bytes(p.st, p.stages, p.chunk_cap);
   const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0, c = g && !q && p.st.cls.run != 0;
-  if (launches) *launches += 4;
+  if (launches) *launches += 5;
   if (g && q) return launch_variant<true, true, false>(p, sms, smem, stream);
   if (c) return launch_variant<true, false, true>(p, sms, smem, stream);
   if (g) return launch_variant<true, false, false>(p, sms, smem, stream);

@@ -38,26 +38,27 @@ enum ScanFlags : uint32_t {
 };
 
 // Geometry of the kernel (compile-time; DESIGN.md "scan kernel").
-constexpr int kScanWarps = 30;                      // warps that scan
-constexpr int kScanThreads = 1024;                  // + finisher warp (30: look-back, copy-out) + producer warp (31: TMA)
+constexpr int kScanWarps = 31;                      // warps that scan
+constexpr int kScanThreads = 1024;                  // + producer warp (31: tickets, TMA)
 constexpr int kTileBytes = 16384;                   // positions per tile
 constexpr int kTilePre = 16;                        // bytes staged in front of a tile (previous byte)
 constexpr int kTileHalo = 112;                      // bytes staged behind a tile
 constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 16512 = 129*128
 constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes: the unit a warp grabs
-constexpr int kTileChunks = kTileBytes / kChunkBytes; // 32: one per lane of the finisher warp
+constexpr int kTileChunks = kTileBytes / kChunkBytes; // 32
 constexpr int kMaxStages = 4;                       // ring of tile buffers
-constexpr int kMaxSets = 8;                         // staging sets (tiles whose matches wait for the finisher)
-constexpr int kInfoRing = 16;                       // >= kMaxStages + kMaxSets
-constexpr uint32_t kChunkCapMin = 16;               // staged matches per chunk: at least ...
-constexpr uint32_t kChunkCapMax = 512;              // ... at most
+constexpr int kInfoRing = 8;                        // tile descriptions in shared memory (>= 2 * kMaxStages)
+constexpr uint32_t kChunkCapMin = 32;               // staged matches per chunk: at least ...
+constexpr uint32_t kChunkCapMax = 1024;             // ... at most
 constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
 constexpr int kQ2Entries = 64;                      // hit queue per warp (u64 entries)
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
-constexpr int kSmemHeader = 3072;                   // barriers, per-tile bookkeeping, stage infos
+constexpr int kSmemHeader = 1024;                   // barriers, stage infos
 constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
+constexpr uint32_t kChunkOverflow = 0x80000000u;    // ChunkDesc::count flag: records are written by redo_kernel
+constexpr uint32_t kPrefixSpan = 4096;              // chunks per block of the prefix / place kernels
 
-struct TileDesc;
+struct ChunkDesc;
 struct ScanParams {
   DeviceStore st;
   // input bytes
@@ -77,15 +78,13 @@ struct ScanParams {
   uint32_t tiles_per_win;
   // tiles
   uint32_t num_tiles;             // tiles of this launch
-  TileDesc *tile_desc;            // [num_tiles] written by the scan, completed by the prefix kernel
-  uint32_t *temp;                 // packed matches (pos_in_tile << 18 | len), one run per tile
-  unsigned long long temp_cap;    // entries (>= result capacity + kTempSlackPerSm * SMs: blocks are not filled to the end)
+  ChunkDesc *chunk_desc;          // [num_tiles * kTileChunks] written by the scan
+  unsigned long long *span_base;  // [ceil(chunks / kPrefixSpan)] sums, then first result index, of every span of chunks
+  uint32_t *temp;                 // packed matches (pos_in_tile << 18 | len), one run per chunk
+  unsigned long long temp_cap;    // entries (result capacity + slack: the warps' blocks are not filled to the end)
   unsigned long long *temp_count; // bump allocator of temp[] (may run past temp_cap: entries are then dropped)
   unsigned int *ticket;           // dynamic tile counter of this launch
-  // tiles whose matches did not fit the staging area; rewritten by redo_kernel
-  uint32_t *redo_list;     // launch-local tile indices
-  unsigned int *redo_count;
-  unsigned long long *out_base; // [num_tiles] first result index of each tile (prefix kernel)
+  unsigned int *redo_flag;        // set when a chunk's matches did not fit its staging area (redo_kernel)
   // output
   Record *out;
   uint64_t out_cap;
@@ -94,30 +93,29 @@ struct ScanParams {
   unsigned long long *counters; // hits, misses, comparisons, long hits (omega_match_stats_t)
   uint32_t flags;
   uint32_t stages;    // ring depth
-  uint32_t sets;      // staging sets
   uint32_t chunk_cap; // staged matches per chunk
 };
 
-// One per tile.  The scan writes count/overflow/temp_base; prefix_kernel adds out_base, the
-// tile's first index in the result array (matches come out in tile order = offset order).
-struct alignas(16) TileDesc {
-  uint32_t count;    // exact number of matches of the tile
-  uint32_t overflow; // 1: the staging area was too small, redo_kernel writes this tile's records
-  unsigned long long temp_base; // first entry of the tile in temp[]
+// One per 512-byte chunk, written by the warp that scanned it.
+struct alignas(8) ChunkDesc {
+  uint32_t count;      // exact number of matches of the chunk (| kChunkOverflow: not in temp[])
+  uint32_t temp_index; // first entry of the chunk's run in temp[]
 };
 
-constexpr uint64_t kTempSlackPerSm = 8192; // see scan.cu kTempBlock
+// temp[] is handed to the scanning warps in blocks; what a warp leaves unused is lost
+constexpr uint32_t kWarpTempBlock = 1024;
+inline uint64_t temp_slack_entries(int sms) { return uint64_t(sms) * kScanWarps * 2 * kWarpTempBlock; }
 
 struct ScanGeometry {
-  uint32_t stages = 0, sets = 0, chunk_cap = 0;
+  uint32_t stages = 0, chunk_cap = 0;
 };
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t sets, uint32_t chunk_cap);
-// chooses ring depth, staging sets and capacity for the shared memory there is; stages == 0 if
-// the filters do not fit at all
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap);
+// chooses ring depth and staging capacity for the shared memory there is; stages == 0 if the
+// filters do not fit at all
 ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit);
-// scan -> prefix over the tile counts -> placement of the records in final order -> redo pass
-// (exits at once when no tile overflowed).  `out_base` [num_tiles] is scratch for the prefix.
+// scan -> prefix over the chunk counts (two kernels) -> placement of the records in final order
+// -> redo pass (exits at once when no chunk overflowed)
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches);
 cudaError_t scan_configure(size_t smem_limit);
 
