@@ -456,66 +456,68 @@ struct Scanner {
                                                    uint32_t lane, uint32_t *stage, uint32_t used, uint32_t cap,
                                                    unsigned long long out_base, unsigned long long emit_base,
                                                    const uint32_t *map, uint32_t *overflow) const {
-    const bool mine = lane < n;
+    bool mine = lane < n;
     const unsigned long long ent = mine ? q2[lane] : 0ull;
     const uint32_t slot = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
     const uint32_t tpos = hi & 0xFFFFu;
     const bool cand_p = (hi >> 16) & 1u;
-    uint32_t cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-    if (mine)
-      verify(T, tpos, slot, cand_p, [&](uint32_t len) {
-        if (cnt == 0) m0 = len;
-        else if (cnt == 1) m1 = len;
-        else if (cnt == 2) m2 = len;
-        else if (cnt == 3) m3 = len;
-        ++cnt;
-      });
-    const uint32_t bal = __ballot_sync(kFull, cnt > 0);
-    if (!bal) return 0;
-    uint32_t pre, tot;
-    const bool many = __any_sync(kFull, cnt > 1);
-    if (!many) {
-      pre = __popc(bal & ((1u << lane) - 1u));
-      tot = __popc(bal);
-    } else {
-      uint32_t in2 = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFull, in2, d);
-        if (lane >= (uint32_t)d) in2 += t;
-      }
-      pre = in2 - cnt;
-      tot = __shfl_sync(kFull, in2, 31);
-    }
-    const uint32_t at = used + pre;
-    auto put = [&](uint32_t i, uint32_t len) {
-      if (MODE == kDirectMode) {
-        const unsigned long long r = out_base + at + i;
-        if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
-      } else if (MODE == kStageMode) {
-        if (at + i < cap && !(len >> kPackLenBits)) {
-          stage[at + i] = (tpos << kPackLenBits) | len;
-        } else {
-          *overflow = 1;
-        }
-      }
-    };
-    if (cnt > 0) put(0, m0);
-    if (cnt > 1) put(1, m1);
-    if (cnt > 2) put(2, m2);
-    if (cnt > 3) put(3, m3);
-    if (MODE != kCountMode && many && __any_sync(kFull, cnt > 4)) {
-      if (cnt > 4) { // evaluate the position again for matches 5, 6, ...
-        uint32_t i = 0;
-        const uint32_t keep = stat_inc;
-        stat_inc = 0;
+    // One copy of verify() in the instruction stream: positions with more than four matches are
+    // evaluated again (skip = 4, 8, ...) by the same code -- rare, and the kernel is I-cache bound.
+    uint32_t at = 0, tot = 0, skip = 0;
+    const uint32_t keep = stat_inc;
+    bool again;
+    do {
+      uint32_t cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+      if (mine)
         verify(T, tpos, slot, cand_p, [&](uint32_t len) {
-          if (i >= 4) put(i, len);
-          ++i;
+          const uint32_t j = cnt - skip; // wraps to a huge value while cnt < skip
+          if (j == 0) m0 = len;
+          else if (j == 1) m1 = len;
+          else if (j == 2) m2 = len;
+          else if (j == 3) m3 = len;
+          ++cnt;
         });
-        stat_inc = keep;
+      if (skip == 0) { // where this lane's matches go: ballot + popc, a shuffle scan only when needed
+        const uint32_t bal = __ballot_sync(kFull, cnt > 0);
+        if (!bal) return 0;
+        uint32_t pre;
+        if (!__any_sync(kFull, cnt > 1)) {
+          pre = __popc(bal & ((1u << lane) - 1u));
+          tot = __popc(bal);
+        } else {
+          uint32_t in2 = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, in2, d);
+            if (lane >= (uint32_t)d) in2 += t;
+          }
+          pre = in2 - cnt;
+          tot = __shfl_sync(kFull, in2, 31);
+        }
+        at = used + pre;
       }
-    }
+      auto put = [&](uint32_t i, uint32_t len) {
+        if (MODE == kDirectMode) {
+          const unsigned long long r = out_base + at + i;
+          if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
+        } else if (MODE == kStageMode) {
+          if (at + i < cap && !(len >> kPackLenBits)) {
+            stage[at + i] = (tpos << kPackLenBits) | len;
+          } else {
+            *overflow = 1;
+          }
+        }
+      };
+      if (cnt > skip) put(skip, m0);
+      if (cnt > skip + 1) put(skip + 1, m1);
+      if (cnt > skip + 2) put(skip + 2, m2);
+      if (cnt > skip + 3) put(skip + 3, m3);
+      skip += 4;
+      stat_inc = 0;
+      mine = mine && cnt > skip;
+      again = MODE != kCountMode && __any_sync(kFull, mine);
+    } while (again);
+    stat_inc = keep;
     return tot;
   }
 
@@ -567,24 +569,27 @@ struct Scanner {
         uint32_t slot;
         const bool want = probe_key(pr[u], &slot);
         const uint32_t bal = __ballot_sync(kFull, want);
-        if (!bal) continue;
         if (want)
-          q2[q2n + __popc(bal & lt)] =
-              ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 4u) << 14)) << 32) | slot;
+          q2[q2n + __popc(bal & lt)] = ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 4u) << 14)) << 32) | slot;
         q2n += __popc(bal);
+      }
+      __syncwarp();
+      // ONE verify_batch in the instruction stream (the kernel is I-cache bound): it runs when 32
+      // entries are waiting, and drains the queue after the last candidates of the chunk
+      const bool last = base + 32 * kProbeUnroll >= total;
+      while (q2n >= 32 || (last && q2n)) {
+        const uint32_t nb = q2n < 32 ? q2n : 32;
+        found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, out_base, emit_base, map, overflow);
+        const uint32_t rest = q2n - nb; // <= 63
+        const unsigned long long mv0 = lane < rest ? q2[32 + lane] : 0ull;
+        const unsigned long long mv1 = 32 + lane < rest ? q2[64 + lane] : 0ull;
         __syncwarp();
-        if (q2n >= 32) {
-          found += verify_batch<MODE>(T, q2, 32, lane, stage, found, cap, out_base, emit_base, map, overflow);
-          const uint32_t rest = q2n - 32;
-          const unsigned long long mv = lane < rest ? q2[32 + lane] : 0ull;
-          __syncwarp();
-          if (lane < rest) q2[lane] = mv;
-          __syncwarp();
-          q2n = rest;
-        }
+        if (lane < rest) q2[lane] = mv0;
+        if (32 + lane < rest) q2[32 + lane] = mv1;
+        __syncwarp();
+        q2n = rest;
       }
     }
-    if (q2n) found += verify_batch<MODE>(T, q2, q2n, lane, stage, found, cap, out_base, emit_base, map, overflow);
     __syncwarp();
     return found;
   }
@@ -711,6 +716,7 @@ struct Scanner {
         kb[u] = make_uint4(empty, empty, empty, empty);
         if (HAS_G4 && pass[u]) kb[u] = __ldg(keys + bucket[u]);
       }
+      static_assert(U == 2, "Q2 holds 31 + 2 x 32 entries");
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (u > 0 && base + u * 32 >= total) break;
@@ -734,19 +740,24 @@ struct Scanner {
               ((unsigned long long)((cbase + e[u]) | (HAS_P23 && shortc[u] ? 0x10000u : 0u)) << 32) | slot;
         }
         q2n += __popc(bal);
+      }
+      __syncwarp();
+      // ONE verify_batch in the instruction stream: it runs when 32 entries are waiting, and
+      // drains the queue after the last candidates of the chunk
+      const bool last = base + 32 * U >= total;
+      while (q2n >= 32 || (last && q2n)) {
+        const uint32_t nb = q2n < 32 ? q2n : 32;
+        found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, out_base, emit_base, map, overflow);
+        const uint32_t rest = q2n - nb; // <= 63
+        const unsigned long long mv0 = lane < rest ? q2[32 + lane] : 0ull;
+        const unsigned long long mv1 = 32 + lane < rest ? q2[64 + lane] : 0ull;
         __syncwarp();
-        if (q2n >= 32) {
-          found += verify_batch<MODE>(T, q2, 32, lane, stage, found, cap, out_base, emit_base, map, overflow);
-          const uint32_t rest = q2n - 32;
-          const unsigned long long mv = lane < rest ? q2[32 + lane] : 0ull;
-          __syncwarp();
-          if (lane < rest) q2[lane] = mv;
-          __syncwarp();
-          q2n = rest;
-        }
+        if (lane < rest) q2[lane] = mv0;
+        if (32 + lane < rest) q2[32 + lane] = mv1;
+        __syncwarp();
+        q2n = rest;
       }
     }
-    if (q2n) found += verify_batch<MODE>(T, q2, q2n, lane, stage, found, cap, out_base, emit_base, map, overflow);
     __syncwarp();
     return found;
   }

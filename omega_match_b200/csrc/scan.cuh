@@ -51,7 +51,7 @@ constexpr int kInfoRing = 8;                        // tile descriptions in shar
 constexpr uint32_t kChunkCapMin = 32;               // staged matches per chunk: at least ...
 constexpr uint32_t kChunkCapMax = 1024;             // ... at most
 constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
-constexpr int kQ2Entries = 64;                      // hit queue per warp (u64 entries)
+constexpr int kQ2Entries = 96;                      // hit queue per warp (u64 entries): 31 left over + 2 x 32 new
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
 constexpr int kSmemHeader = 1024;                   // barriers, stage infos
 constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
