@@ -357,6 +357,8 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     e2e_step()
+    if rank == 0:
+        log(f"[bench] e2e call breakdown (device events, ms): {m.last_timing()}")
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

@@ -162,7 +162,7 @@ omega_match_results_t *omega_list_matcher_match(const omega_list_matcher_t *m, c
 
 void omega_match_results_destroy(omega_match_results_t *results) {
   if (!results) return;
-  std::free(results->matches);
+  if (!olm::pinned_result_release(results->matches)) std::free(results->matches);
   results->matches = nullptr;
   results->count = 0;
   std::free(results);

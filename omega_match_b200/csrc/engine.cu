@@ -406,7 +406,7 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   results->matches = static_cast<omega_match_result_t *>(std::malloc(sizeof(omega_match_result_t)));
   if (n == 0 || !haystack) return results;
   auto bail = [&]() -> omega_match_results_t * {
-    std::free(results->matches);
+    if (!pinned_result_release(results->matches)) std::free(results->matches);
     std::free(results);
     return nullptr;
   };
@@ -456,7 +456,10 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   E.last.h2d_ms = ms;
   if (dres.count) {
     std::free(results->matches);
-    results->matches = static_cast<omega_match_result_t *>(std::malloc(dres.count * sizeof(omega_match_result_t)));
+    const size_t rbytes = dres.count * sizeof(omega_match_result_t);
+    results->matches = nullptr;
+    if (rbytes >= kPinnedResultMin) results->matches = static_cast<omega_match_result_t *>(pinned_result_alloc(rbytes));
+    if (!results->matches) results->matches = static_cast<omega_match_result_t *>(std::malloc(rbytes));
     if (!results->matches) {
       std::free(results);
       return nullptr;

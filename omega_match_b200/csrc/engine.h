@@ -24,6 +24,11 @@ struct ScanRange {
   uint64_t match_ptr_base = 0;
 };
 
+// Large result arrays of the host API (cuda_util.cu): pinned, recycled across calls.
+void *pinned_result_alloc(size_t bytes);
+bool pinned_result_release(void *p); // false: not one of ours (plain malloc)
+constexpr size_t kPinnedResultMin = size_t(1) << 20;
+
 struct EngineImpl;
 
 class Engine {
