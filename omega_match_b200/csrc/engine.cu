@@ -93,7 +93,7 @@ struct EngineImpl {
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, chunk_desc, span_base, temp, misc, norm, map, windows, ghost, fscratch;
+  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, misc, norm, map, windows, ghost, fscratch;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -172,7 +172,7 @@ Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
-                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->misc,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->misc,
                     &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch})
     b->release();
   for (auto &ev : impl_->ev)
@@ -244,6 +244,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     if (E.norm.ensure(kNormFront + bw * kWinStride + 256)) return -1;
     if (!identity_map && E.map.ensure(bw * uint64_t(kWindowBytes) * 4)) return -1;
     if (E.windows.ensure(n_windows * sizeof(WindowDesc))) return -1;
+    if (!identity_map && E.tfblocks.ensure(bw * kTfBlocksPerWindow * sizeof(TfBlock))) return -1;
   }
 
   uint64_t cap = std::max<uint64_t>(E.out_hint, n_own / 64 + 4096);
@@ -328,6 +329,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         T.win_stride = kWinStride;
         T.map = identity_map ? nullptr : static_cast<uint32_t *>(E.map.p);
         T.windows = static_cast<WindowDesc *>(E.windows.p) + w0;
+        T.blocks = static_cast<TfBlock *>(E.tfblocks.p);
         T.ghost = static_cast<uint8_t *>(E.ghost.p);
         T.flags = E.hdr.flags;
         OLM_CUDA(transform_launch(T, nw, E.has_short_234, E.sms, E.stream, &launches));
