@@ -39,6 +39,7 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 constexpr uint32_t kTfBlockBytes = kTfThreads * 16;                 // 16 KiB
 constexpr uint32_t kTfBlocksPerWin = kWindowBytes / kTfBlockBytes;   // 256
+constexpr size_t kTfWriteSmem = (kTfBlockBytes + 32) + (kTfBlockBytes + 8) * 4; // staged bytes + staged map
 
 // One 16 KiB block of a window.  WRITE = false: summary with carry 0 -> P.blocks[].
 // WRITE = true: carry and offset from P.blocks[] (resolved), bytes and map written.
@@ -181,15 +182,46 @@ __global__ void __launch_bounds__(kTfThreads, 1) transform_block_kernel(Transfor
     }
     return;
   }
-  uint32_t o = out_base + warp_excl + (incl - cnt);
-  // scatter kept bytes and their source indices
-  uint32_t kk = keep;
-  while (kk) {
-    const uint32_t k = __ffs(kk) - 1;
-    kk &= kk - 1;
-    out[o] = (uint8_t)(mapped[k >> 2] >> (8 * (k & 3)));
-    if (map) map[o] = i0 + k;
-    ++o;
+  // Kept bytes and their source indices go through shared memory so that the global stores are
+  // 16-byte vectors: the staging offset is chosen congruent to the global offset mod 16 bytes.
+  extern __shared__ __align__(16) uint8_t tf_smem[];
+  uint8_t *s_bytes = tf_smem;                                                   // kTfBlockBytes + 32
+  uint32_t *s_map = reinterpret_cast<uint32_t *>(tf_smem + kTfBlockBytes + 32); // kTfBlockBytes + 8 entries
+  const uint32_t ab = out_base & 15u, am = out_base & 3u; // alignment of the block's first byte / map entry
+  {
+    uint32_t o = warp_excl + (incl - cnt); // block-relative
+    uint32_t kk = keep;
+    while (kk) {
+      const uint32_t k = __ffs(kk) - 1;
+      kk &= kk - 1;
+      s_bytes[ab + o] = (uint8_t)(mapped[k >> 2] >> (8 * (k & 3)));
+      if (map) s_map[am + o] = i0 + k;
+      ++o;
+    }
+  }
+  __syncthreads();
+  {
+    // bytes: global range [out_base, out_base + block_total) = staging range [ab, ab + block_total)
+    uint8_t *gdst = out + (out_base - ab); // 16-byte aligned
+    const uint32_t end = ab + block_total;
+    for (uint32_t v = tid * 16; v < end; v += kTfThreads * 16) {
+      if (v >= ab && v + 16 <= end) {
+        *reinterpret_cast<uint4 *>(gdst + v) = *reinterpret_cast<const uint4 *>(s_bytes + v);
+      } else {
+        for (uint32_t j = v < ab ? ab : v; j < v + 16 && j < end; ++j) gdst[j] = s_bytes[j];
+      }
+    }
+    if (map) {
+      uint32_t *mdst = map + (out_base - am); // 16-byte aligned
+      const uint32_t mend = am + block_total;
+      for (uint32_t v = tid * 4; v < mend; v += kTfThreads * 4) {
+        if (v >= am && v + 4 <= mend) {
+          *reinterpret_cast<uint4 *>(mdst + v) = *reinterpret_cast<const uint4 *>(s_map + v);
+        } else {
+          for (uint32_t j = v < am ? am : v; j < v + 4 && j < mend; ++j) mdst[j] = s_map[j];
+        }
+      }
+    }
   }
 }
 
@@ -334,13 +366,20 @@ __global__ void fold_case_kernel(TransformParams P, uint32_t n_windows) {
 cudaError_t transform_launch(const TransformParams &p, uint32_t n_windows, bool need_tails, int sms,
                              cudaStream_t stream, uint32_t *launches) {
   if (n_windows == 0) return cudaSuccess;
+  static bool configured = false; // the write pass stages 80 KB in dynamic shared memory
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(transform_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kTfWriteSmem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
   const bool fold_only = (p.flags & kFlagAnyTransform) == kFlagIgnoreCase;
   if (fold_only) {
     fold_case_kernel<<<sms * 4, 512, 0, stream>>>(p, n_windows);
   } else {
     transform_block_kernel<false><<<n_windows * kTfBlocksPerWin, kTfThreads, 0, stream>>>(p);
     transform_resolve_kernel<<<(n_windows + 3) / 4, 128, 0, stream>>>(p, n_windows);
-    transform_block_kernel<true><<<n_windows * kTfBlocksPerWin, kTfThreads, 0, stream>>>(p);
+    transform_block_kernel<true><<<n_windows * kTfBlocksPerWin, kTfThreads, kTfWriteSmem, stream>>>(p);
     *launches += 2;
   }
   ++*launches;
