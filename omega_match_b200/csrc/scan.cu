@@ -41,6 +41,7 @@
 //     writes their records directly at the index place_kernel computed.
 #include "scan.cuh"
 
+#include <cstddef>
 #include <cstdio>
 
 #include "olm_classes.h"
@@ -123,17 +124,73 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// Shared memory by 32-bit shared-space address.  The scanning warps never dereference a generic
+// pointer into shared memory: every generic access makes nvcc recompute the shared window base
+// (S2R SR_CgaCtaId + LEA, on the slow XU pipe) -- ~35 of them per chunk saturated that pipe.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long lds64u(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64u(uint32_t a, unsigned long long v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
 // little-endian 32-bit word at an arbitrary shared-memory byte address
-__device__ __forceinline__ uint32_t lds_le32(const uint8_t *q) {
-  const uint32_t a = smem_u32(q);
-  uint32_t lo, hi;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a & ~3u));
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"((a & ~3u) + 4));
-  return __funnelshift_r(lo, hi, (a & 3u) * 8u);
+__device__ __forceinline__ uint32_t lds_le32(uint32_t a) {
+  const uint32_t lo = lds32(a & ~3u), hi = lds32((a & ~3u) + 4);
+  return __funnelshift_r(lo, hi, a << 3);
+}
+__device__ __forceinline__ void mbar_arrive32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 struct TileCtx {
-  const uint8_t *sb; // stage buffer; sb[kTilePre + i] is the byte at tile position i
+  uint32_t sb32;     // stage buffer (shared-space address); byte sb32 + kTilePre + i is tile position i
   unsigned long long p0;
   long long boff;
   uint32_t rem0;   // min(len - p0, 2^31): bytes of the segment from the tile's first position on
@@ -176,7 +233,7 @@ struct Scanner {
       : P(p), g4s(g4), p23s(p23), fl(p.flags) {}
 
   __device__ __forceinline__ uint32_t hay_byte(const TileCtx &T, uint32_t rel) const {
-    if (rel < T.staged) return T.sb[kTilePre + rel];
+    if (rel < T.staged) return lds8(T.sb32 + kTilePre + rel);
     return P.buf[T.boff + (long long)rel];
   }
 
@@ -236,12 +293,12 @@ struct Scanner {
     pr.bucket = 0;
     pr.kb = make_uint4(0, 0, 0, 0);
     if (!valid) return;
-    const uint8_t *q = T.sb + kTilePre + tpos;
+    const uint32_t q = T.sb32 + kTilePre + tpos;
     if (fl & (kWordBoundary | kWordPrefix | kLineStart)) {
       const bool at0 = T.first && tpos == 0;
-      const uint32_t prev = q[-1];
+      const uint32_t prev = lds8(q - 1);
       if (fl & kWordBoundary) { // matcher.c:770-776
-        const bool cw = is_word_byte(q[0]);
+        const bool cw = is_word_byte(lds8(q));
         const bool pw = at0 ? false : is_word_byte(prev);
         if (cw == pw) return;
       }
@@ -288,7 +345,7 @@ struct Scanner {
   template <typename Emit>
   __device__ __forceinline__ void verify(const TileCtx &T, uint32_t tpos, uint32_t slot, bool cand_p, Emit &&emit) const {
     const uint32_t rem = T.rem0 - tpos;
-    const uint8_t *q = T.sb + kTilePre + tpos;
+    const uint32_t q = T.sb32 + kTilePre + tpos;
     bool emitted = false;
     const bool longest = fl & kLongestOnly;
 
@@ -407,12 +464,12 @@ struct Scanner {
 
   // stage 1 for one lane: 16 positions -> candidate masks (bit k = position lpos + k)
   __device__ __forceinline__ void stage1(const TileCtx &T, uint32_t lpos, uint32_t &cg, uint32_t &cp) const {
-    const uint8_t *src = T.sb + kTilePre + lpos;
-    const uint4 v = *reinterpret_cast<const uint4 *>(src);
+    const uint32_t src = T.sb32 + kTilePre + lpos;
+    const uint4 v = lds128(src);
     cg = 0;
     cp = 0;
     if (HAS_CLS) {
-      const uint2 nx = *reinterpret_cast<const uint2 *>(src + 16);
+      const uint2 nx = lds64(src + 16);
       // bit i = byte lpos+i is in the class, i < 24
       uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
                    (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
@@ -427,7 +484,7 @@ struct Scanner {
       cg = a & 0xFFFFu;
       return;
     }
-    const uint32_t w4 = *reinterpret_cast<const uint32_t *>(src + 16);
+    const uint32_t w4 = lds32(src + 16);
     const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -452,12 +509,12 @@ struct Scanner {
   //   kCountMode : nothing is written;
   //   kDirectMode: matches go to P.out[out_base ...] as final records.
   template <int MODE>
-  __device__ __forceinline__ uint32_t verify_batch(const TileCtx &T, const unsigned long long *q2, uint32_t n,
-                                                   uint32_t lane, uint32_t *stage, uint32_t used, uint32_t cap,
+  __device__ __forceinline__ uint32_t verify_batch(const TileCtx &T, uint32_t q2, uint32_t n, uint32_t lane,
+                                                   uint32_t stage, uint32_t used, uint32_t cap,
                                                    unsigned long long out_base, unsigned long long emit_base,
                                                    const uint32_t *map, uint32_t *overflow) const {
     bool mine = lane < n;
-    const unsigned long long ent = mine ? q2[lane] : 0ull;
+    const unsigned long long ent = mine ? lds64u(q2 + 8u * lane) : 0ull; // q2, stage: shared-space addresses
     const uint32_t slot = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
     const uint32_t tpos = hi & 0xFFFFu;
     const bool cand_p = (hi >> 16) & 1u;
@@ -502,7 +559,7 @@ struct Scanner {
           if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
         } else if (MODE == kStageMode) {
           if (at + i < cap && !(len >> kPackLenBits)) {
-            stage[at + i] = (tpos << kPackLenBits) | len;
+            sts32(stage + 4u * (at + i), (tpos << kPackLenBits) | len);
           } else {
             *overflow = 1;
           }
@@ -525,8 +582,8 @@ struct Scanner {
   // verify batches.  Returns the exact number of matches of the chunk in all modes.
   static constexpr int kProbeUnroll = 2;
   template <int MODE>
-  __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t *stage,
-                                                 uint32_t cap, uint16_t *q1, unsigned long long *q2,
+  __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t stage,
+                                                 uint32_t cap, uint32_t q1, uint32_t q2,
                                                  unsigned long long out_base, unsigned long long emit_base,
                                                  const uint32_t *map, uint32_t *overflow) const {
     uint32_t cg, cp;
@@ -548,7 +605,7 @@ struct Scanner {
       while (cand) {
         const uint32_t k = __ffs(cand) - 1;
         cand &= cand - 1;
-        q1[o++] = (uint16_t)((lane * 16 + k) | (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10));
+        sts16(q1 + 2u * o++, (lane * 16 + k) | (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10));
       }
     }
     __syncwarp();
@@ -560,7 +617,7 @@ struct Scanner {
       for (int u = 0; u < kProbeUnroll; ++u) {
         const uint32_t idx = base + u * 32 + lane;
         const bool ok = idx < total;
-        const uint32_t e = ok ? q1[idx] : 0u;
+        const uint32_t e = ok ? lds16(q1 + 2u * idx) : 0u;
         probe_issue(T, ok, cbase + (e & 511u), (e >> 9) & 1u, (e >> 10) & 1u, pr[u]);
       }
 #pragma unroll
@@ -570,7 +627,8 @@ struct Scanner {
         const bool want = probe_key(pr[u], &slot);
         const uint32_t bal = __ballot_sync(kFull, want);
         if (want)
-          q2[q2n + __popc(bal & lt)] = ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 4u) << 14)) << 32) | slot;
+          sts64u(q2 + 8u * (q2n + __popc(bal & lt)),
+                 ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 4u) << 14)) << 32) | slot);
         q2n += __popc(bal);
       }
       __syncwarp();
@@ -581,11 +639,11 @@ struct Scanner {
         const uint32_t nb = q2n < 32 ? q2n : 32;
         found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, out_base, emit_base, map, overflow);
         const uint32_t rest = q2n - nb; // <= 63
-        const unsigned long long mv0 = lane < rest ? q2[32 + lane] : 0ull;
-        const unsigned long long mv1 = 32 + lane < rest ? q2[64 + lane] : 0ull;
+        const unsigned long long mv0 = lane < rest ? lds64u(q2 + 8u * (32 + lane)) : 0ull;
+        const unsigned long long mv1 = 32 + lane < rest ? lds64u(q2 + 8u * (64 + lane)) : 0ull;
         __syncwarp();
-        if (lane < rest) q2[lane] = mv0;
-        if (32 + lane < rest) q2[32 + lane] = mv1;
+        if (lane < rest) sts64u(q2 + 8u * lane, mv0);
+        if (32 + lane < rest) sts64u(q2 + 8u * (32 + lane), mv1);
         __syncwarp();
         q2n = rest;
       }
@@ -597,20 +655,20 @@ struct Scanner {
   // The same chunk for the common case -- no position predicate requested, no 1..3 byte
   // patterns -- written against raw shared-memory offsets with nothing but the essentials in
   // the per-candidate rounds (the generic scan_chunk above spends ~3x the instructions there).
-  //   sb_off/g4_off/q1_off/q2_off: byte offsets into the CTA's dynamic shared memory.
+  //   sb_off/g4_off/p23_off/q1_off/q2_off/stage: shared-space byte addresses.
   template <int MODE>
-  __device__ __forceinline__ uint32_t scan_chunk_fast(const TileCtx &T, uint8_t *smem_base, uint32_t sb_off,
-                                                      uint32_t g4_off, uint32_t p23_off, uint32_t q1_off,
-                                                      uint32_t q2_off, uint32_t cbase, uint32_t lane, uint32_t *stage,
-                                                      uint32_t cap, unsigned long long out_base,
+  __device__ __forceinline__ uint32_t scan_chunk_fast(const TileCtx &T, uint32_t sb_off, uint32_t g4_off,
+                                                      uint32_t p23_off, uint32_t q1_off, uint32_t q2_off,
+                                                      uint32_t cbase, uint32_t lane, uint32_t stage, uint32_t cap,
+                                                      unsigned long long out_base,
                                                       unsigned long long emit_base, const uint32_t *map,
                                                       uint32_t *overflow) const {
     const uint32_t lpos = cbase + lane * 16;
     const uint32_t src = sb_off + kTilePre + lpos;
-    const uint4 v = *reinterpret_cast<const uint4 *>(smem_base + src);
+    const uint4 v = lds128(src);
     uint32_t cand = 0, cp = 0; // cp: candidates of the 1..3 byte patterns (HAS_P23)
     if (HAS_CLS) {
-      const uint2 nx = *reinterpret_cast<const uint2 *>(smem_base + src + 16);
+      const uint2 nx = lds64(src + 16);
       uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
                    (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
                    (gather4(class_word(nx.y)) << 20);
@@ -622,7 +680,7 @@ struct Scanner {
       if (have < P.st.cls.run) a &= a >> (P.st.cls.run - have);
       cand = a & 0xFFFFu;
     } else {
-      const uint32_t w4 = *reinterpret_cast<const uint32_t *>(smem_base + src + 16);
+      const uint32_t w4 = lds32(src + 16);
       const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
       const uint32_t sh = P.st.g4_shift;
       const uint32_t pand = P.st.p23_and, pmul = P.st.p23_mul, psh = P.st.p23_shift;
@@ -631,12 +689,12 @@ struct Scanner {
         const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
         if (HAS_G4) {
           const uint32_t b = (gram * kHashMul) >> sh;
-          const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + g4_off + ((b >> 5) << 2));
+          const uint32_t word = lds32(g4_off + ((b >> 5) << 2));
           cand |= ((word >> (b & 31)) & 1u) << k;
         }
         if (HAS_P23) {
           const uint32_t b = ((gram & pand) * pmul) >> psh;
-          const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + p23_off + ((b >> 5) << 2));
+          const uint32_t word = lds32(p23_off + ((b >> 5) << 2));
           cp |= ((word >> (b & 31)) & 1u) << k;
         }
       }
@@ -662,7 +720,7 @@ struct Scanner {
           if ((cand >> k) & 1u) { // entry: position | gram candidate << 9 | short candidate << 10
             uint32_t ent = eb + k;
             if (HAS_P23) ent |= (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10);
-            *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)ent;
+            sts16(qa, ent);
             qa += 2;
           }
       } else {
@@ -671,19 +729,20 @@ struct Scanner {
           const uint32_t k = __ffs(cand) - 1;
           uint32_t ent = eb + k;
           if (HAS_P23) ent |= (((cg >> k) & 1u) << 9) | (((cp >> k) & 1u) << 10);
-          *reinterpret_cast<uint16_t *>(smem_base + qa) = (uint16_t)ent;
+          sts16(qa, ent);
           cand &= cand - 1;
           qa += 2;
         }
       }
     }
     __syncwarp();
-    unsigned long long *q2 = reinterpret_cast<unsigned long long *>(smem_base + q2_off);
+    const uint32_t q2 = q2_off;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t tile_off = sb_off + kTilePre + cbase;
     const uint32_t key_shift = P.st.key_shift, g4_shift = P.st.g4_shift, empty = P.st.empty_key;
     const uint4 *keys = P.st.keys;
     const uint32_t rem_c = T.rem0 - cbase; // >= 1
+    const bool near_end = rem_c < (uint32_t)kChunkBytes + 4u;
     uint32_t found = 0, q2n = 0;
     constexpr int U = OLM_FAST_UNROLL;
     for (uint32_t base = 0; base < total; base += 32 * U) {
@@ -694,7 +753,7 @@ struct Scanner {
       for (int u = 0; u < U; ++u) {
         const uint32_t idx = base + u * 32 + lane;
         pass[u] = idx < total;
-        e[u] = pass[u] ? *reinterpret_cast<const uint16_t *>(smem_base + q1_off + 2u * idx) : 0u;
+        e[u] = pass[u] ? lds16(q1_off + 2u * idx) : 0u;
         shortc[u] = false;
         if (HAS_P23) { // unpack the flags; without a gram candidate there is no key probe
           shortc[u] = (e[u] >> 10) & 1u;
@@ -702,19 +761,16 @@ struct Scanner {
           e[u] &= 511u;
         }
         const uint32_t a = tile_off + e[u];
-        const uint32_t lo = *reinterpret_cast<const uint32_t *>(smem_base + (a & ~3u));
-        const uint32_t hi = *reinterpret_cast<const uint32_t *>(smem_base + (a & ~3u) + 4);
-        gram[u] = __byte_perm(__funnelshift_r(lo, hi, a << 3), 0, 0x0123);
+        gram[u] = __byte_perm(lds_le32(a), 0, 0x0123);
         const uint32_t h = gram[u] * kHashMul;
-        pass[u] = pass[u] && (e[u] + 4u <= rem_c);
+        if (near_end) pass[u] = pass[u] && (e[u] + 4u <= rem_c); // only the segment's last chunks
         if (HAS_CLS) {
           const uint32_t b = h >> g4_shift;
-          const uint32_t word = *reinterpret_cast<const uint32_t *>(smem_base + g4_off + ((b >> 5) << 2));
+          const uint32_t word = lds32(g4_off + ((b >> 5) << 2));
           pass[u] = pass[u] && ((word >> (b & 31)) & 1u);
         }
         bucket[u] = h >> key_shift;
-        kb[u] = make_uint4(empty, empty, empty, empty);
-        if (HAS_G4 && pass[u]) kb[u] = __ldg(keys + bucket[u]);
+        if (HAS_G4 && pass[u]) kb[u] = __ldg(keys + bucket[u]); // (not read when !pass[u])
       }
       static_assert(U == 2, "Q2 holds 31 + 2 x 32 entries");
 #pragma unroll
@@ -733,12 +789,11 @@ struct Scanner {
         const bool want = hit || (HAS_P23 && shortc[u]);
         const uint32_t bal = __ballot_sync(kFull, want);
         if (!bal) continue;
-        if (want) {
-          uint32_t slot = kNoSlot;
-          if (hit) slot = 4u * bucket[u] + (kb[u].x == g ? 0u : kb[u].y == g ? 1u : kb[u].z == g ? 2u : 3u);
-          q2[q2n + __popc(bal & lt)] =
-              ((unsigned long long)((cbase + e[u]) | (HAS_P23 && shortc[u] ? 0x10000u : 0u)) << 32) | slot;
-        }
+        // (branch-free: the slot of a miss is kNoSlot, the store is predicated)
+        const uint32_t place = kb[u].y == g ? 1u : kb[u].z == g ? 2u : kb[u].w == g ? 3u : 0u;
+        const uint32_t slot = hit ? 4u * bucket[u] + place : kNoSlot;
+        const uint32_t hi32 = (cbase + e[u]) | (HAS_P23 && shortc[u] ? 0x10000u : 0u);
+        if (want) sts64u(q2 + 8u * (q2n + __popc(bal & lt)), ((unsigned long long)hi32 << 32) | slot);
         q2n += __popc(bal);
       }
       __syncwarp();
@@ -749,11 +804,11 @@ struct Scanner {
         const uint32_t nb = q2n < 32 ? q2n : 32;
         found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, out_base, emit_base, map, overflow);
         const uint32_t rest = q2n - nb; // <= 63
-        const unsigned long long mv0 = lane < rest ? q2[32 + lane] : 0ull;
-        const unsigned long long mv1 = 32 + lane < rest ? q2[64 + lane] : 0ull;
+        const unsigned long long mv0 = lane < rest ? lds64u(q2 + 8u * (32 + lane)) : 0ull;
+        const unsigned long long mv1 = 32 + lane < rest ? lds64u(q2 + 8u * (64 + lane)) : 0ull;
         __syncwarp();
-        if (lane < rest) q2[lane] = mv0;
-        if (32 + lane < rest) q2[32 + lane] = mv1;
+        if (lane < rest) sts64u(q2 + 8u * lane, mv0);
+        if (32 + lane < rest) sts64u(q2 + 8u * (32 + lane), mv1);
         __syncwarp();
         q2n = rest;
       }
@@ -836,8 +891,8 @@ __device__ __forceinline__ void start_tile(const ScanParams &P, uint32_t t, Stag
   copy_tile(P, I, dst, bar);
 }
 
-__device__ __forceinline__ void tile_ctx(const StageInfo &I, const uint8_t *sb, TileCtx &T) {
-  T.sb = sb;
+__device__ __forceinline__ void tile_ctx(const StageInfo &I, uint32_t sb32, TileCtx &T) {
+  T.sb32 = sb32;
   T.p0 = I.p0;
   T.boff = I.boff;
   T.rem0 = I.rem0;
@@ -947,50 +1002,68 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   }
 
   // ================================ scanning warps ================================
+  // (everything in shared memory is addressed by 32-bit shared-space addresses from here on)
   Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
-  uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
-  unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
-  uint32_t *my_stage = L.staging + (size_t)warp * cap;
-  const uint32_t ring_off = (uint32_t)(L.ring - smem), g4_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
-  const uint32_t p23_off = (uint32_t)(reinterpret_cast<uint8_t *>(L.p23s) - smem);
-  const uint32_t q1_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q1) - smem);
-  const uint32_t q2_off = (uint32_t)(reinterpret_cast<uint8_t *>(my_q2) - smem);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t ring32 = sbase + (uint32_t)(L.ring - smem);
+  const uint32_t g4_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
+  const uint32_t p23_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.p23s) - smem);
+  const uint32_t q1_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.q1 + warp * kChunkBytes) - smem);
+  const uint32_t q2_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.q2 + warp * kQ2Entries) - smem);
+  const uint32_t stage32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.staging + (size_t)warp * cap) - smem);
+  const uint32_t hdr32 = sbase; // SmemHeader
+  const uint32_t full32 = hdr32 + (uint32_t)offsetof(SmemHeader, full);
+  const uint32_t scanned32 = hdr32 + (uint32_t)offsetof(SmemHeader, scanned);
+  const uint32_t ctr32 = hdr32 + (uint32_t)offsetof(SmemHeader, chunk_ctr);
+  const uint32_t endk32 = hdr32 + (uint32_t)offsetof(SmemHeader, end_k);
+  const uint32_t info32 = hdr32 + (uint32_t)offsetof(SmemHeader, info);
   unsigned long long blk_next = 0; // this warp's block of temp[]: next free entry ...
   uint32_t blk_left = 0;           // ... and how many are left
   for (;;) {
     uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(&H.chunk_ctr, 1u);
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(ctr32) : "memory");
     c = __shfl_sync(kFull, c, 0);
     const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
     const uint32_t s = k & (S - 1), gen = k >> (S == 4 ? 2 : 1); // S is 2 or 4
-    const StageInfo &I = H.info[k % kInfoRing];
+    const uint32_t I32 = info32 + (k % kInfoRing) * (uint32_t)sizeof(StageInfo);
     // The mbarrier only tells two phases apart: make sure the stage is in OUR generation first.
     // (Chunks past the CTA's last tile may belong to an iteration that is never produced.)
     bool over = false;
-    while (ld_volatile_shared(&I.seq) != k) {
-      if (k >= ld_volatile_shared(&H.end_k)) {
+    while (lds32(I32 + (uint32_t)offsetof(StageInfo, seq)) != k) {
+      if (k >= lds32(endk32)) {
         over = true;
         break;
       }
       __nanosleep(32);
     }
     if (over) break;
-    mbar_wait(&H.full[s], gen & 1u);
-    const uint32_t tile = I.tile;
+    mbar_wait32(full32 + 8u * s, gen & 1u);
+    const uint32_t tile = lds32(I32 + (uint32_t)offsetof(StageInfo, tile));
     if (tile == kNoTile) break;
     TileCtx T;
-    tile_ctx(I, L.ring + (size_t)s * kStageBytes, T);
+    {
+      const uint2 p0 = lds64(I32 + (uint32_t)offsetof(StageInfo, p0));
+      const uint2 bo = lds64(I32 + (uint32_t)offsetof(StageInfo, boff));
+      T.sb32 = ring32 + s * (uint32_t)kStageBytes;
+      T.p0 = ((unsigned long long)p0.y << 32) | p0.x;
+      T.boff = (long long)(((unsigned long long)bo.y << 32) | bo.x);
+      T.rem0 = lds32(I32 + (uint32_t)offsetof(StageInfo, rem0));
+      T.nscan = lds32(I32 + (uint32_t)offsetof(StageInfo, nscan));
+      T.staged = lds32(I32 + (uint32_t)offsetof(StageInfo, staged));
+      T.tail = lds32(I32 + (uint32_t)offsetof(StageInfo, tail));
+      T.first = (p0.x | p0.y) == 0;
+    }
     const uint32_t cbase = ci * kChunkBytes;
     uint32_t n = 0, ovf = 0;
     if (cbase < T.nscan) {
       if (FAST)
-        n = sc.template scan_chunk_fast<kStageMode>(T, smem, ring_off + s * kStageBytes, g4_off, p23_off, q1_off, q2_off,
-                                                    cbase, lane, my_stage, cap, 0, 0, nullptr, &ovf);
+        n = sc.template scan_chunk_fast<kStageMode>(T, T.sb32, g4_32, p23_32, q1_32, q2_32, cbase, lane, stage32, cap, 0,
+                                                    0, nullptr, &ovf);
       else
-        n = sc.template scan_chunk<kStageMode>(T, cbase, lane, my_stage, cap, my_q1, my_q2, 0, 0, nullptr, &ovf);
+        n = sc.template scan_chunk<kStageMode>(T, cbase, lane, stage32, cap, q1_32, q2_32, 0, 0, nullptr, &ovf);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&H.scanned[s]); // the stage buffer is not read any more
+    if (lane == 0) mbar_arrive32(scanned32 + 8u * s); // the stage buffer is not read any more
     // ---- hand the chunk over: descriptor, and the staged matches into this warp's run of temp[]
     ovf = __any_sync(kFull, ovf != 0);
     ChunkDesc d;
@@ -1010,7 +1083,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       // (when temp[] is too small the entries are dropped; the host sees it and repeats the call)
       if (blk_next + n <= P.temp_cap && blk_next + n <= 0xFFFFFFFFull) {
         uint32_t *dst = P.temp + blk_next;
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = my_stage[i];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = lds32(stage32 + 4u * i);
       }
       d.temp_index = (uint32_t)blk_next;
       blk_next += n;
@@ -1018,7 +1091,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     }
     if (lane == 0)
       *reinterpret_cast<uint2 *>(P.chunk_desc + ((size_t)tile * kTileChunks + ci)) = make_uint2(d.count, d.temp_index);
-    __syncwarp(); // my_stage is rewritten by the next chunk
+    __syncwarp(); // the staging area is rewritten by the next chunk
   }
   sc.flush_stats(lane);
 }
@@ -1060,7 +1133,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
       const uint32_t cbase = ci * kChunkBytes;
       // the chunk as a tile of its own: position 0 = the chunk's first byte
       TileCtx T;
-      T.sb = buf;
+      T.sb32 = smem_u32(buf);
       T.p0 = I.p0 + cbase;
       T.boff = I.boff + cbase;
       T.rem0 = I.rem0 - cbase;
@@ -1084,7 +1157,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
         base += part;
       }
       const uint32_t *map = use_map ? P.map + (size_t)I.win * kWindowBytes : nullptr;
-      sc.template scan_chunk<kDirectMode>(T, 0, lane, nullptr, 0, my_q1, my_q2, base, I.emit_base, map, nullptr);
+      sc.template scan_chunk<kDirectMode>(T, 0, lane, 0u, 0, smem_u32(my_q1), smem_u32(my_q2), base, I.emit_base, map, nullptr);
       __syncwarp();
     }
   }
