@@ -7,7 +7,7 @@
 // concatenate + radix sort of finalize_match_results (matcher.c:587-623, :258-325).
 //
 // Shape of scan_kernel
-//   * persistent CTAs (grid = #SMs) of 32 warps: 31 scanning warps and one producer warp.  Tiles of 16 KiB positions are handed out by an atomic ticket, so tile k
+//   * persistent CTAs (grid = #SMs) of 32 warps: 31 scanning warps and one producer warp.  Tiles of 8 KiB positions are handed out by an atomic ticket, so tile k
 //     is always started before k+1; inside a CTA the 32 chunks (512 positions) of a tile are
 //     grabbed dynamically by the scanning warps -- no warp waits for a slower one;
 //   * producer: each tile (+16 bytes in front, +112 behind) is brought into shared memory by
@@ -1024,7 +1024,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(ctr32) : "memory");
     c = __shfl_sync(kFull, c, 0);
     const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
-    const uint32_t s = k & (S - 1), gen = k >> (S == 4 ? 2 : 1); // S is 2 or 4
+    const uint32_t s = k & (S - 1), gen = k >> (31 - __clz(S)); // S is 2, 4 or 8
     const uint32_t I32 = info32 + (k % kInfoRing) * (uint32_t)sizeof(StageInfo);
     // The mbarrier only tells two phases apart: make sure the stage is in OUR generation first.
     // (Chunks past the CTA's last tile may belong to an iteration that is never produced.)
@@ -1100,12 +1100,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 // such chunks, copies the chunk (+ the bytes around it) into a small private buffer, evaluates
 // it again and writes final records at the index place_kernel left in the descriptor.
 constexpr int kRedoBuf = kTilePre + kChunkBytes + kTileHalo; // 640
+constexpr uint32_t kRedoStages = (kScanWarps * kRedoBuf + kStageBytes - 1) / kStageBytes; // "ring" space for the buffers
 template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
 __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (*P.redo_flag == 0) return;
   // header | "ring": one 640-byte buffer per warp | g4 | p23 | Q2 | Q1
-  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, 2, 0);
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, kRedoStages, 0);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t fl = P.flags;
   load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
@@ -1115,7 +1116,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
   sc.stat_inc = 0; // the main pass has counted these chunks already
   uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
   unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
-  uint8_t *buf = L.ring + (size_t)warp * kRedoBuf; // 31 * 640 < 2 * kStageBytes
+  uint8_t *buf = L.ring + (size_t)warp * kRedoBuf;
   const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
   const uint64_t n_chunks = (uint64_t)P.num_tiles * kTileChunks;
   // a warp looks at 32 descriptors at a time and takes the flagged chunks one after the other
@@ -1292,7 +1293,7 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   place_kernel<<<n_spans, kPrefixThreads, 0, stream>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, 2, 0), stream>>>(p);
+  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, kRedoStages, 0), stream>>>(p);
   return cudaGetLastError();
 }
 
