@@ -350,6 +350,7 @@ def run_ours(args):
             lib.omega_match_results_destroy(res)
         else:
             hay[:own_len].copy_(host[:own_len], non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the library scans on its own stream
             c, ptr = m.match_shard(hay.data_ptr(), sh.slice_begin, own_len, sh.own_begin, sh.own_end, total, 0, **mflags)
             if c:
                 out = torch.as_tensor(DevArray(ptr, c), device=dev).to("cpu")

@@ -172,7 +172,10 @@ int olm_cuda_set_default_device(int device);
 int olm_cuda_matcher_device(const omega_list_matcher_t *matcher);
 
 /* Same as omega_list_matcher_match() but the haystack is DEVICE memory on the matcher's GPU
- * (16-byte aligned, readable up to the next multiple of 16) and the results stay there.
+ * (16-byte aligned, readable up to the next multiple of 16) and the results stay there.  The
+ * kernels run on a stream owned by the matcher; the call first waits for all work queued on the
+ * device (so bytes produced on any other stream are complete) and returns after its own kernels
+ * have finished.
  * `match_ptr_base` is the address written into record.match (+offset); pass the device
  * pointer itself or the host address the bytes came from.  Returns 0, or -1 on a CUDA error. */
 int olm_cuda_match_device(const omega_list_matcher_t *matcher, const void *dev_haystack,

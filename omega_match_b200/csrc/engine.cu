@@ -190,6 +190,8 @@ const olm_cuda_timing_t &Engine::timing() const { return impl_->last; }
 int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_results_t *res) {
   EngineImpl &E = *impl_;
   OLM_CUDA(cudaSetDevice(E.device));
+  // device-resident input may have been produced on any stream of the caller
+  if (!E.streaming) OLM_CUDA(cudaDeviceSynchronize());
   res->count = 0;
   res->records = nullptr;
   res->device = E.device;

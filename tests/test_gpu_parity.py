@@ -405,6 +405,7 @@ def test_large_synthetic_properties(store_cache):
         for s in shard_plan(n, 4, 24, False):
             sl = torch.zeros(((s.slice_end - s.slice_begin + 15) // 16) * 16 + 16, dtype=torch.uint8, device="cuda")
             sl[:s.slice_end - s.slice_begin] = hay[s.slice_begin:s.slice_end]
+            torch.cuda.synchronize()  # the library scans on its own stream: the bytes must be there
             c2, p2 = m.match_shard(sl.data_ptr(), s.slice_begin, s.slice_end - s.slice_begin, s.own_begin, s.own_end,
                                    n, 0)
             parts.append(_device_records(torch, p2, c2))
@@ -518,3 +519,56 @@ def test_streaming_host_path_matches_device_path(store_cache):
             got = m.match_arrays(host, longest_only=True)
             assert same_matches(got, dev), describe_diff(got, dev)
             assert cnt > 100_000
+
+
+def test_config5_at_full_size(store_cache):
+    """BASELINE configs[4] at its full size -- 16 GiB synthetic haystack x 1,000,000 patterns --
+    through size-independent properties: every planted pattern is reported (one per 4 KiB
+    block), offsets ascend with lengths strictly descending inside an offset, reported bytes are
+    patterns, two byte-range shards give the identical record stream, and a 2 MiB slice in the
+    middle agrees with the oracle record by record."""
+    torch = pytest.importorskip("torch")
+    import synth_torch
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~45 GB of free device memory")
+    pats = inputs.synth_long_patterns(1_000_000)
+    path = store_cache("cfg5-1m", b"\n".join(pats))
+    n = 16 << 30
+    hay = synth_torch.synth_haystack_torch(n, inputs.SEED_H5, device="cuda")
+    pb, pl = synth_torch.pack_patterns(pats, "cuda")
+    planted = synth_torch.plant_torch(hay, pb, pl, inputs.SEED_H5 ^ 0x77)
+    del pb, pl
+    with Matcher(path) as m:
+        cnt, ptr = m.match_device(hay.data_ptr(), n)
+        rec = _device_records(torch, ptr, cnt).clone()
+        off, ln = rec[:, 0], rec[:, 1] & 0xFFFFFFFF
+        assert cnt >= planted == n // 4096
+        assert bool((off[1:] >= off[:-1]).all())
+        same_off = off[1:] == off[:-1]
+        assert bool((ln[1:][same_off] < ln[:-1][same_off]).all())
+        assert torch.unique(off // 4096).numel() == planted
+        sample = torch.randint(0, cnt, (500,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+        pset = set(pats)
+        for o_, l_ in zip(off[sample].tolist(), ln[sample].tolist()):
+            assert hay[o_:o_ + l_].cpu().numpy().tobytes() in pset
+        whole_digest = Oracle.stream_digest(_as_matches(rec))
+        # two shards, each from its own copy of its slice (+ halo), as two GPUs would hold them
+        parts = []
+        for s in shard_plan(n, 2, 24, False):
+            sl = torch.zeros(((s.slice_end - s.slice_begin + 15) // 16) * 16 + 16, dtype=torch.uint8, device="cuda")
+            sl[:s.slice_end - s.slice_begin] = hay[s.slice_begin:s.slice_end]
+            torch.cuda.synchronize()  # the library scans on its own stream: the bytes must be there
+            c2, p2 = m.match_shard(sl.data_ptr(), s.slice_begin, s.slice_end - s.slice_begin, s.own_begin, s.own_end,
+                                   n, 0)
+            parts.append(_device_records(torch, p2, c2).clone())
+            del sl
+        assert Oracle.stream_digest(_as_matches(torch.cat(parts))) == whole_digest
+        # a slice across the shard boundary against the oracle (matches that start inside it)
+        lo = (n // 2) - (1 << 20)
+        piece = hay[lo:lo + (2 << 20)].cpu().numpy()
+        want = Oracle.from_olm(path).match(piece)
+        got = m.match_arrays(piece)
+        assert same_matches(got, want), describe_diff(got, want)
+        inside = (off >= lo) & (off + ln <= lo + (2 << 20))
+        assert int(inside.sum()) == want.size
