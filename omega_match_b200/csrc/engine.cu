@@ -1,15 +1,18 @@
 // engine.cu -- sequencing of one match call on one GPU.
 //
 //   no transform flag in the store (matcher.c:939-943):
-//       [memset descriptors] -> scan_kernel over the owned byte range -> (no_overlap filter)
+//       scan -> prefix -> place -> redo over the owned byte range (one launch group; the host
+//       path runs one group per 256 MiB segment while later segments are still being copied)
+//       -> (no_overlap filter)
 //   transform flag (matcher.c:945-1018): for every batch of <= kBatchWindows source windows
-//       transform (normalise, offset map, window descriptors) -> window tails -> scan_kernel
-//       over the normalised windows, the decoupled look-back continuing across batches so the
-//       records of all windows come out in one ordered array -> (no_overlap filter)
+//       transform (count / resolve / write: normalised bytes, offset map, window descriptors)
+//       -> window tails -> scan -> prefix -> place -> redo over the normalised windows; the
+//       running match total carries over from batch to batch, so the records of all windows
+//       come out in one ordered array -> (no_overlap filter)
 //
-// The scan writes final records; the only host synchronisation of a call is the read-back of
-// the record count (needed to size the D2H copy / to detect a too small result buffer, in
-// which case the buffer is grown to the exact count and the call repeated).
+// place_kernel / redo_kernel write final records; the only host synchronisation of a call is the
+// read-back of the record count (needed to size the D2H copy / to detect a too small result or
+// temp buffer, in which case the buffers are grown to the exact size and the call repeated).
 #include "engine.h"
 
 #include <algorithm>
