@@ -214,13 +214,14 @@ typedef struct {
   uint32_t len1, len2, len3, len4;
   uint64_t store_bytes, file_bytes;
   /* how the store is staged for the GPU (device_tables.h) */
-  uint32_t gram_keys;      /* distinct 4-byte grams in the key table */
+  uint32_t gram_keys;      /* distinct keys in the key table */
   uint32_t key_buckets;    /* 16-byte buckets of that table */
   uint32_t g4_bits;        /* bits of the shared-memory gram bitmap */
   uint32_t class_run;      /* byte-class prefilter: leading pattern bytes tested (0 = off) */
   uint32_t class_and_mask; /* 0x7f, or 0x5f when bit 5 is folded (case) */
   uint32_t class_ranges;   /* 1 or 2 */
   uint32_t class_lo[2], class_hi[2];
+  uint32_t key_bytes;      /* leading pattern bytes a key covers (4..8) */
 } olm_store_info_t;
 int olm_store_inspect(const char *compiled_file, olm_store_info_t *out);
 

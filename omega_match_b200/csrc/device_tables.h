@@ -4,19 +4,23 @@
 // slots, so nothing of the file is used in place.  At create() the store is
 // re-staged into:
 //
-//   keys[]    the exact gram set: BUCKETS of four 32-bit grams (16 bytes, one vector load).  A
-//             gram lives in the first bucket, counted from its home bucket, that had a free
-//             place when it was inserted; places fill left to right, so a bucket whose last
-//             place holds `empty_key` ends a probe.  Load <= 0.25: a probe -- hit or miss --
-//             costs one 16-byte load in ~98% of the cases.  This is the table almost every
-//             candidate dies in, so it holds nothing but keys (role of probe_bucket,
-//             hash_table.c:91-109).  `empty_key` is a value that is not a gram of the store.
+//   keys[]    the key set: BUCKETS of four 32-bit keys (16 bytes, one vector load).  A key is
+//             key_hash() of the first K = key_bytes bytes of a pattern, K = 4 when the store has
+//             4-byte patterns, else min(shortest pattern, 8): at 1 M random patterns a third of
+//             the candidates share the first FOUR bytes with some pattern but almost none the
+//             first six, so nearly every probe ends in this table.  (Two different prefixes may
+//             hash to the same key -- ~n^2 / 2^33 pairs -- they then share a slot and are told
+//             apart by the byte compare.)  A key lives in the first bucket, counted from its
+//             home bucket, that had a free place when it was inserted; places fill left to
+//             right, so a bucket whose last place holds `empty_key` ends a probe.  Load <= 0.25:
+//             a probe -- hit or miss -- costs one 16-byte load in ~98% of the cases (role of
+//             probe_bucket, hash_table.c:91-109).  `empty_key` is a value that is no key.
 //   slots[]   parallel to keys[] (slot = 4*bucket + place), read only after a key hit: pattern
-//             bytes 4..11 and the length of the (single) pattern, so that a pattern of up to
-//             12 bytes is verified without touching the pattern store, or a reference to
-//   recs[]    for grams shared by several patterns: 16-byte records, longest first (the order
+//             bytes 0..7 and the length of the (single) pattern, so that a pattern of up to 8
+//             bytes is verified without touching the pattern store, or a reference to
+//   recs[]    for keys shared by several patterns: 16-byte records, longest first (the order
 //             compiler.c:271 gives the bucket).  Grams of 4-byte patterns live in the same
-//             table (flag bit) -> the length-4 short matcher (matcher.c:685-692, a binary
+//             table (flag bit, K = 4) -> the length-4 short matcher (matcher.c:685-692, a binary
 //             search) becomes the same probe.
 //   store[]   pattern bytes, padded so 4-byte reads never leave the allocation.
 //   g4[]      single-probe hashed bitmap over every gram in keys[] -- a superset filter with
@@ -38,23 +42,32 @@
 namespace olm {
 
 struct alignas(16) Slot {
-  uint32_t next4; // pattern bytes 4..7 as a little-endian word, zero padded (single-pattern slots)
-  uint32_t next8; // pattern bytes 8..11, same
-  uint32_t meta;  // 0 = empty; see kSlot* below
-  uint32_t ref;   // single: offset of the pattern in store[]; multi: first index in recs[]
+  uint32_t w0;   // pattern bytes 0..3 as a little-endian word (single-pattern slots)
+  uint32_t w1;   // pattern bytes 4..7, zero padded
+  uint32_t meta; // 0 = empty; see kSlot* below
+  uint32_t ref;  // single: offset of the pattern in store[]; multi: first index in recs[]
 };
 constexpr uint32_t kSlotShort4 = 1u << 31;   // a 4-byte pattern equals this gram
 constexpr uint32_t kSlotMulti = 1u << 30;    // low bits = number of recs, else = pattern length (0: none)
 constexpr uint32_t kSlotValueMask = (1u << 30) - 1;
 
 struct alignas(16) Rec {
-  uint32_t next4;
+  uint32_t w0; // bytes 0..3
   uint32_t len;
   uint32_t store_off;
-  uint32_t next8;
+  uint32_t w1; // bytes 4..7, zero padded
 };
 
-constexpr uint32_t kHashMul = 0x9E3779B1u; // one multiply feeds both the g4 filter and the bucket index
+constexpr uint32_t kHashMul = 0x9E3779B1u; // one hash feeds both the g4 filter and the bucket index
+constexpr uint32_t kHashMul2 = 0x85EBCA6Bu;
+
+// Key of a pattern prefix / haystack position: `gram` = bytes 0..3 packed big-endian
+// (util.h:23-26), `tail` = bytes 4..7 as a little-endian word, masked to the key_bytes - 4
+// bytes that belong to the key (0 for 4-byte keys: then the key is a bijection of the gram).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t key_hash(uint32_t gram, uint32_t tail) { return (gram * kHashMul) ^ (tail * kHashMul2); }
 
 // Byte-class prefilter: byte b is in the class iff, with t = b & and_mask (and_mask clears bit 7
 // and optionally bit 5), lo[i] <= t <= hi[i] for one of the n_ranges ranges, and b < 0x80.
@@ -79,9 +92,11 @@ struct DeviceStore {
   const uint32_t *set3 = nullptr;    // open addressing, value = key3 + 1, 0 = empty
   const uint32_t *bitmap2 = nullptr; // 2048 words, bit (b0<<8|b1) as in short_matcher_t
   uint32_t bitmap1[8] = {0};         // bit b as in short_matcher_t
-  uint32_t key_shift = 32;           // home bucket = (gram*kHashMul) >> key_shift
+  uint32_t key_shift = 32;           // home bucket = key >> key_shift
   uint32_t key_mask = 0;             // number of buckets - 1
   uint32_t empty_key = 0;
+  uint32_t key_bytes = 4;            // K: pattern bytes a key covers (4..8)
+  uint32_t tail_mask = 0;            // the K - 4 low bytes of the little-endian word of bytes 4..7
   uint32_t g4_shift = 32, g4_words = 0;
   uint32_t p23_and = 0, p23_mul = 1, p23_shift = 32, p23_words = 0;
   uint32_t set3_mask = 0;

@@ -237,10 +237,10 @@ struct Scanner {
     return P.buf[T.boff + (long long)rel];
   }
 
-  // bytes [12, len) of a candidate against the pattern store (bytes 0..11 are already equal)
+  // bytes [8, len) of a candidate against the pattern store (bytes 0..7 are already equal)
   __device__ __forceinline__ bool tail_equal(const TileCtx &T, uint32_t tpos, uint32_t len, uint32_t store_off) const {
     const uint8_t *pat = P.st.store + store_off;
-    for (uint32_t i = 12; i < len; ++i)
+    for (uint32_t i = 8; i < len; ++i)
       if (hay_byte(T, tpos + i) != __ldg(pat + i)) return false;
     return true;
   }
@@ -281,7 +281,7 @@ struct Scanner {
   //               `emit(len)` is called once per accepted match, longest first.
   static constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
   struct Probe {
-    uint32_t tpos, gram, bucket, flags; // flags: 1 = alive, 2 = gram candidate (and >= 4 bytes left), 4 = short candidate
+    uint32_t tpos, gram, bucket, flags; // gram: the position's key; flags: 1 = alive, 2 = key candidate (enough bytes left), 4 = short candidate
     uint4 kb;
   };
 
@@ -306,10 +306,10 @@ struct Scanner {
       if ((fl & kLineStart) && !at0 && !is_line_end_byte(prev)) return; // :196, :807
     }
     const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
-    pr.gram = gram;
     pr.flags = 1u | (cand_p ? 4u : 0u);
-    if (HAS_G4 && cand_g && T.rem0 - tpos >= 4) {
-      const uint32_t h = gram * kHashMul;
+    if (HAS_G4 && cand_g && T.rem0 - tpos >= P.st.key_bytes) {
+      const uint32_t h = key_hash(gram, P.st.tail_mask ? lds_le32(q + 4) & P.st.tail_mask : 0u);
+      pr.gram = h; // the key of the position
       if (HAS_CLS) { // Q1 holds class survivors: the gram bitmap is probed here
         const uint32_t b = h >> P.st.g4_shift;
         if (!((g4s[b >> 5] >> (b & 31)) & 1u)) return;
@@ -353,18 +353,15 @@ struct Scanner {
       const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + slot));
       const uint32_t meta = s.z; // 0 when the gram equals empty_key and matched an unused place
       if (meta != 0) {
-        const uint32_t hay4 = lds_le32(q + 4), hay8 = lds_le32(q + 8);
+        const unsigned long long hay = ((unsigned long long)lds_le32(q + 4) << 32) | lds_le32(q);
         if (meta & kSlotValueMask) {
           n_hits += stat_inc;
           n_long_hits += stat_inc;
         }
-        // bytes 4..11 of a pattern of length len against the haystack
-        const unsigned long long hay48 = ((unsigned long long)hay8 << 32) | hay4;
-        auto head_equal = [&](uint32_t len, uint32_t n4, uint32_t n8) {
-          // the first min(len, 12) - 4 bytes of the 8-byte window, via one 64-bit shift
-          const uint32_t drop = len >= 12 ? 0u : (12u - len) * 8u; // bits of the window beyond the pattern
-          const unsigned long long diff = (hay48 ^ (((unsigned long long)n8 << 32) | n4)) << drop;
-          return diff == 0;
+        // bytes 0..7 of a pattern of length len (>= 5) against the haystack, one 64-bit compare
+        auto head_equal = [&](uint32_t len, uint32_t w0, uint32_t w1) {
+          const uint32_t drop = len >= 8 ? 0u : (8u - len) * 8u; // bits of the window beyond the pattern
+          return ((hay ^ (((unsigned long long)w1 << 32) | w0)) << drop) == 0;
         };
         if (meta & kSlotMulti) {
           const uint32_t cnt = meta & kSlotValueMask;
@@ -374,7 +371,7 @@ struct Scanner {
             if (len > rem) continue; // matcher.c:203
             n_cmp += stat_inc;
             if (!head_equal(len, r.x, r.w)) continue;
-            if (len > 12 && !tail_equal(T, tpos, len, r.z)) continue;
+            if (len > 8 && !tail_equal(T, tpos, len, r.z)) continue;
             if (!end_ok_long(T, tpos, len)) continue;
             emit(len);
             emitted = true;
@@ -384,7 +381,7 @@ struct Scanner {
           const uint32_t len = meta & kSlotValueMask;
           if (len != 0 && len <= rem) {
             n_cmp += stat_inc;
-            if (head_equal(len, s.x, s.y) && (len <= 12 || tail_equal(T, tpos, len, s.w)) &&
+            if (head_equal(len, s.x, s.y) && (len <= 8 || tail_equal(T, tpos, len, s.w)) &&
                 end_ok_long(T, tpos, len)) {
               emit(len);
               emitted = true;
@@ -484,13 +481,16 @@ struct Scanner {
       cg = a & 0xFFFFu;
       return;
     }
-    const uint32_t w4 = lds32(src + 16);
-    const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
+    const uint2 w45 = lds64(src + 16);
+    const uint32_t w[6] = {v.x, v.y, v.z, v.w, w45.x, w45.y};
+    const uint32_t tmask = P.st.tail_mask;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
       if (HAS_G4) {
-        const uint32_t b = (gram * kHashMul) >> P.st.g4_shift;
+        // (keys longer than 4 bytes: the little-endian word of bytes k+4..k+7 joins the hash)
+        const uint32_t tail = __byte_perm(w[(k >> 2) + 1], w[(k >> 2) + 2 > 5 ? 5 : (k >> 2) + 2], 0x3210u + 0x1111u * (k & 3));
+        const uint32_t b = key_hash(gram, tail & tmask) >> P.st.g4_shift;
         cg |= ((g4s[b >> 5] >> (b & 31)) & 1u) << k;
       }
       if (HAS_P23) {
@@ -680,15 +680,22 @@ struct Scanner {
       if (have < P.st.cls.run) a &= a >> (P.st.cls.run - have);
       cand = a & 0xFFFFu;
     } else {
-      const uint32_t w4 = lds32(src + 16);
-      const uint32_t w[5] = {v.x, v.y, v.z, v.w, w4};
-      const uint32_t sh = P.st.g4_shift;
+      const uint2 w45 = lds64(src + 16);
+      const uint32_t w[6] = {v.x, v.y, v.z, v.w, w45.x, w45.y};
+      const uint32_t sh = P.st.g4_shift, tmask = P.st.tail_mask;
       const uint32_t pand = P.st.p23_and, pmul = P.st.p23_mul, psh = P.st.p23_shift;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const uint32_t gram = __byte_perm(w[k >> 2], w[(k >> 2) + 1], 0x0123u + 0x1111u * (k & 3));
         if (HAS_G4) {
-          const uint32_t b = (gram * kHashMul) >> sh;
+          // (keys longer than 4 bytes: the little-endian word of bytes k+4..k+7 joins the hash;
+          // stores with 1..3 byte patterns always have 4-byte keys)
+          uint32_t hk = gram * kHashMul;
+          if (!HAS_P23) {
+            const uint32_t tail = __byte_perm(w[(k >> 2) + 1], w[(k >> 2) + 2 > 5 ? 5 : (k >> 2) + 2], 0x3210u + 0x1111u * (k & 3));
+            hk ^= (tail & tmask) * kHashMul2;
+          }
+          const uint32_t b = hk >> sh;
           const uint32_t word = lds32(g4_off + ((b >> 5) << 2));
           cand |= ((word >> (b & 31)) & 1u) << k;
         }
@@ -742,7 +749,8 @@ struct Scanner {
     const uint32_t key_shift = P.st.key_shift, g4_shift = P.st.g4_shift, empty = P.st.empty_key;
     const uint4 *keys = P.st.keys;
     const uint32_t rem_c = T.rem0 - cbase; // >= 1
-    const bool near_end = rem_c < (uint32_t)kChunkBytes + 4u;
+    const uint32_t tmask = P.st.tail_mask, kbytes = P.st.key_bytes;
+    const bool near_end = rem_c < (uint32_t)kChunkBytes + 8u;
     uint32_t found = 0, q2n = 0;
     constexpr int U = OLM_FAST_UNROLL;
     for (uint32_t base = 0; base < total; base += 32 * U) {
@@ -761,9 +769,10 @@ struct Scanner {
           e[u] &= 511u;
         }
         const uint32_t a = tile_off + e[u];
-        gram[u] = __byte_perm(lds_le32(a), 0, 0x0123);
-        const uint32_t h = gram[u] * kHashMul;
-        if (near_end) pass[u] = pass[u] && (e[u] + 4u <= rem_c); // only the segment's last chunks
+        uint32_t h = __byte_perm(lds_le32(a), 0, 0x0123) * kHashMul;
+        if (tmask) h ^= (lds_le32(a + 4) & tmask) * kHashMul2; // keys longer than 4 bytes
+        gram[u] = h; // the key of the position
+        if (near_end) pass[u] = pass[u] && (e[u] + kbytes <= rem_c); // only the segment's last chunks
         if (HAS_CLS) {
           const uint32_t b = h >> g4_shift;
           const uint32_t word = lds32(g4_off + ((b >> 5) << 2));

@@ -118,92 +118,129 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     buckets.push_back(b);
     p += 8 + uint64_t(b.count) * kBucketRecordBytes;
   }
-  if (n_recs_multi > kSlotValueMask) return "too many patterns";
+  (void)n_recs_multi;
 
   // ---- pattern bytes, padded for unaligned 4-byte reads
   s->store.assign(size_t(h.store_bytes) + 16, 0);
   if (h.store_bytes) std::memcpy(s->store.data(), v.patterns, size_t(h.store_bytes));
 
-  // ---- keys + slots: bucket grams first, then the 4-byte patterns are merged in
-  const uint64_t n_keys_upper = buckets.size() + uint64_t(v.n4);
-  // buckets of four places; #buckets >= #keys, i.e. load <= 0.25 (see device_tables.h)
-  uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, n_keys_upper)));
-  if (lg_buckets > 27) return "too many distinct grams";
-  const uint32_t n_buckets = 1u << lg_buckets;
+  // ---- keys + slots.  A key covers the first K bytes of a pattern (device_tables.h).
+  uint32_t min_long = 0xFFFFFFFFu;
+  for (const BucketRef &b : buckets)
+    for (uint32_t j = 0; j < b.count; ++j) min_long = std::min(min_long, rd32(b.recs + 16ull * j + 8));
   DeviceStore &d = s->params;
-  d.key_shift = 32 - lg_buckets;
-  d.key_mask = n_buckets - 1;
-  {
-    // a value no gram of the store equals marks unused places
-    std::vector<uint32_t> all;
-    all.reserve(n_keys_upper);
-    for (const BucketRef &b : buckets) all.push_back(b.gram);
-    for (uint32_t i = 0; i < v.n4; ++i) all.push_back(rd32(v.arr4 + 4ull * i));
-    std::sort(all.begin(), all.end());
-    uint32_t e = 0xFFFFFFFFu;
-    while (std::binary_search(all.begin(), all.end(), e)) --e;
-    d.empty_key = e;
-  }
-  s->keys.assign(n_buckets, make_uint4(d.empty_key, d.empty_key, d.empty_key, d.empty_key));
-  s->slots.assign(size_t(n_buckets) * 4, Slot{0, 0, 0, 0});
-  s->recs.reserve(n_recs_multi);
+  // (stores with 1..4 byte patterns keep 4-byte keys: the 4-byte patterns are keys themselves, and
+  // the kernels for short-pattern stores hash four bytes only)
+  d.key_bytes = (v.n1 || v.n2 || v.n3 || v.n4 || buckets.empty()) ? 4u : std::min<uint32_t>(8u, min_long);
+  d.tail_mask = d.key_bytes >= 8 ? 0xFFFFFFFFu : ((1u << (8 * (d.key_bytes - 4))) - 1u);
 
   auto word_of = [&](uint64_t off, uint32_t len, uint32_t from) {
     uint32_t w = 0;
     for (uint32_t i = 0; i < 4 && from + i < len; ++i) w |= uint32_t(s->store[off + from + i]) << (8 * i);
     return w;
   };
-  // returns the slot of `gram`, claiming the first free place from its home bucket on
-  auto find_or_claim = [&](uint32_t gram, bool *fresh) -> Slot & {
-    for (uint32_t b = key_home(d, gram);; b = (b + 1) & d.key_mask) {
+  // every long pattern with its key, grouped by key in order of first appearance
+  struct Pat {
+    uint32_t key, len;
+    uint64_t off;
+  };
+  std::vector<Pat> pats;
+  pats.reserve(n_long);
+  for (const BucketRef &b : buckets)
+    for (uint32_t j = 0; j < b.count; ++j) {
+      const uint64_t po = rd64(b.recs + 16ull * j);
+      const uint32_t pl = rd32(b.recs + 16ull * j + 8);
+      pats.push_back(Pat{key_hash(b.gram, word_of(po, pl, 4) & d.tail_mask), pl, po});
+    }
+  std::vector<uint32_t> all; // distinct keys (patterns and 4-byte grams)
+  all.reserve(pats.size() + v.n4);
+  for (const Pat &p : pats) all.push_back(p.key);
+  for (uint32_t i = 0; i < v.n4; ++i) all.push_back(key_hash(rd32(v.arr4 + 4ull * i), 0));
+  std::sort(all.begin(), all.end());
+  all.erase(std::unique(all.begin(), all.end()), all.end());
+  const uint64_t n_keys_total = all.size();
+  // buckets of four places; #buckets >= #keys, i.e. load <= 0.25
+  uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, n_keys_total)));
+  if (lg_buckets > 27) return "too many distinct keys";
+  const uint32_t n_buckets = 1u << lg_buckets;
+  d.key_shift = 32 - lg_buckets;
+  d.key_mask = n_buckets - 1;
+  {
+    uint32_t e = 0xFFFFFFFFu; // a value that is no key marks unused places
+    while (std::binary_search(all.begin(), all.end(), e)) --e;
+    d.empty_key = e;
+  }
+  s->keys.assign(n_buckets, make_uint4(d.empty_key, d.empty_key, d.empty_key, d.empty_key));
+  s->slots.assign(size_t(n_buckets) * 4, Slot{0, 0, 0, 0});
+
+  // returns the slot index of `key`, claiming the first free place from its home bucket on
+  auto find_or_claim = [&](uint32_t key, bool *fresh) -> size_t {
+    for (uint32_t b = key_home(d, key);; b = (b + 1) & d.key_mask) {
       uint32_t *k = reinterpret_cast<uint32_t *>(&s->keys[b]);
       for (uint32_t j = 0; j < 4; ++j) {
-        if (k[j] == gram || k[j] == d.empty_key) {
-          *fresh = k[j] != gram;
-          k[j] = gram;
-          return s->slots[4 * size_t(b) + j];
+        if (k[j] == key || k[j] == d.empty_key) {
+          *fresh = k[j] != key;
+          k[j] = key;
+          return 4 * size_t(b) + j;
         }
       }
     }
   };
-  uint32_t n_keys = 0;
-  for (const BucketRef &b : buckets) {
-    bool fresh = false;
-    Slot &sl = find_or_claim(b.gram, &fresh);
-    if (!fresh) return "gram appears in two buckets";
-    ++n_keys;
-    if (b.count == 1) {
-      const uint64_t po = rd64(b.recs);
-      const uint32_t pl = rd32(b.recs + 8);
-      sl.meta = pl;
-      sl.ref = uint32_t(po);
-      sl.next4 = word_of(po, pl, 4);
-      sl.next8 = word_of(po, pl, 8);
+  // patterns per slot, in order of appearance; then single slots inline, the rest through recs[]
+  std::vector<std::vector<uint32_t>> members; // indices into pats, per claimed slot (dense ids)
+  std::vector<size_t> slot_of_group;
+  {
+    std::vector<uint32_t> group_of_slot(s->slots.size(), 0xFFFFFFFFu);
+    for (uint32_t i = 0; i < pats.size(); ++i) {
+      bool fresh = false;
+      const size_t si = find_or_claim(pats[i].key, &fresh);
+      if (group_of_slot[si] == 0xFFFFFFFFu) {
+        group_of_slot[si] = uint32_t(members.size());
+        members.emplace_back();
+        slot_of_group.push_back(si);
+      }
+      members[group_of_slot[si]].push_back(i);
+    }
+  }
+  uint64_t n_multi = 0;
+  for (const auto &m : members)
+    if (m.size() > 1) n_multi += m.size();
+  if (n_multi > kSlotValueMask) return "too many patterns";
+  s->recs.reserve(n_multi);
+  for (size_t g = 0; g < members.size(); ++g) {
+    Slot &sl = s->slots[slot_of_group[g]];
+    const auto &m = members[g];
+    if (m.size() == 1) {
+      const Pat &p = pats[m[0]];
+      sl.meta = p.len;
+      sl.ref = uint32_t(p.off);
+      sl.w0 = word_of(p.off, p.len, 0);
+      sl.w1 = word_of(p.off, p.len, 4);
     } else {
-      sl.meta = kSlotMulti | b.count;
+      sl.meta = kSlotMulti | uint32_t(m.size());
       sl.ref = uint32_t(s->recs.size());
       const size_t first = s->recs.size();
-      for (uint32_t j = 0; j < b.count; ++j) {
-        const uint64_t po = rd64(b.recs + 16ull * j);
-        const uint32_t pl = rd32(b.recs + 16ull * j + 8);
-        s->recs.push_back(Rec{word_of(po, pl, 4), pl, uint32_t(po), word_of(po, pl, 8)});
+      for (uint32_t i : m) {
+        const Pat &p = pats[i];
+        s->recs.push_back(Rec{word_of(p.off, p.len, 0), p.len, uint32_t(p.off), word_of(p.off, p.len, 4)});
       }
-      // the scan emits a bucket's matches in record order and relies on "longest first"
-      // (compiler.c:271 sorts the bucket that way; enforce it for foreign writers)
+      // the scan emits a slot's matches in record order and relies on "longest first"
+      // (compiler.c:271 sorts a bucket that way; patterns that can match at the same position
+      // share their first K bytes, hence their slot)
       std::stable_sort(s->recs.begin() + first, s->recs.end(), [](const Rec &x, const Rec &y) { return x.len > y.len; });
     }
   }
   for (uint32_t i = 0; i < v.n4; ++i) {
     bool fresh = false;
-    Slot &sl = find_or_claim(rd32(v.arr4 + 4ull * i), &fresh);
-    if (fresh) ++n_keys;
+    Slot &sl = s->slots[find_or_claim(key_hash(rd32(v.arr4 + 4ull * i), 0), &fresh)];
     sl.meta |= kSlotShort4;
   }
-  s->n_keys = n_keys;
+  s->n_keys = uint32_t(n_keys_total);
   if (s->recs.empty()) s->recs.push_back(Rec{0, 0, 0, 0}); // never dereferenced; keeps the upload non-empty
 
   // ---- g4: one bit per gram, >= 16 bits per key while it fits the shared-memory budget
-  if (n_keys) {
+  if (s->n_keys) {
+    const uint32_t n_keys = s->n_keys;
     const uint32_t lg = std::min(budget.g4_max_log2, std::max<uint32_t>(10, ceil_log2(uint64_t(n_keys) * 16)));
     d.g4_shift = 32 - lg;
     d.g4_words = (1u << lg) / 32;
@@ -211,7 +248,7 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     for (const uint4 &kb : s->keys)
       for (uint32_t k : {kb.x, kb.y, kb.z, kb.w})
         if (k != d.empty_key) {
-          const uint32_t b = g4_bit(d, k);
+          const uint32_t b = g4_bit(d, k); // k is a key already
           s->g4[b >> 5] |= 1u << (b & 31);
         }
   }
@@ -356,15 +393,16 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
 uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
   const DeviceStore &d = s.params;
   uint64_t bad = 0;
-  auto probe = [&](uint32_t gram) -> const Slot * {
+  // the probe of the scan kernel: bitmap, then the key buckets from the key's home on
+  auto probe = [&](uint32_t key) -> const Slot * {
     if (!s.g4.empty()) {
-      const uint32_t b = g4_bit(d, gram);
+      const uint32_t b = g4_bit(d, key);
       if (!(s.g4[b >> 5] >> (b & 31) & 1)) return nullptr;
     }
-    for (uint32_t b = key_home(d, gram);; b = (b + 1) & d.key_mask) {
+    for (uint32_t b = key_home(d, key);; b = (b + 1) & d.key_mask) {
       const uint32_t *k = reinterpret_cast<const uint32_t *>(&s.keys[b]);
       for (uint32_t j = 0; j < 4; ++j)
-        if (k[j] == gram) return gram == d.empty_key ? nullptr : &s.slots[4 * size_t(b) + j];
+        if (k[j] == key) return key == d.empty_key ? nullptr : &s.slots[4 * size_t(b) + j];
       if (k[3] == d.empty_key) return nullptr;
     }
   };
@@ -373,37 +411,40 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
       if (!class_has(d.cls, p[i])) return false;
     return true;
   };
+  auto le_word = [&](uint64_t po, uint32_t pl, uint32_t from) {
+    uint32_t w = 0;
+    for (uint32_t i = 0; i < 4 && from + i < pl; ++i) w |= uint32_t(v.patterns[po + from + i]) << (8 * i);
+    return w;
+  };
   for (uint64_t p = 0; p < v.hdr.blob_bytes;) {
     const uint32_t gram = rd32(v.blob + p), count = rd32(v.blob + p + 4);
-    const Slot *sl = probe(gram);
     for (uint32_t j = 0; j < count; ++j) {
       const uint64_t po = rd64(v.blob + p + 8 + 16ull * j);
       const uint32_t pl = rd32(v.blob + p + 8 + 16ull * j + 8);
-      bool ok = false;
-      if (sl && !(sl->meta & kSlotMulti))
-        ok = count == 1 && (sl->meta & kSlotValueMask) == pl && sl->ref == po;
-      uint32_t got = sl ? sl->next4 : 0;
-      if (sl && (sl->meta & kSlotMulti) && (sl->meta & kSlotValueMask) == count) {
-        for (uint32_t q = 0; q < count && !ok; ++q) {
+      const uint32_t w0 = le_word(po, pl, 0), w1 = le_word(po, pl, 4);
+      bool ok = pl >= d.key_bytes;
+      const Slot *sl = ok ? probe(key_hash(gram, w1 & d.tail_mask)) : nullptr;
+      ok = sl != nullptr;
+      if (ok && !(sl->meta & kSlotMulti)) {
+        ok = (sl->meta & kSlotValueMask) == pl && sl->ref == po && sl->w0 == w0 && sl->w1 == w1;
+      } else if (ok) {
+        const uint32_t n = sl->meta & kSlotValueMask;
+        bool found = false;
+        for (uint32_t q = 0; q < n; ++q) {
           const Rec &rc = s.recs[sl->ref + q];
-          if (rc.len == pl && rc.store_off == po) {
-            ok = (q == 0 || s.recs[sl->ref + q - 1].len >= rc.len);
-            got = rc.next4;
-          }
+          if (q > 0 && s.recs[sl->ref + q - 1].len < rc.len) ok = false; // longest first
+          if (rc.len == pl && rc.store_off == po) found = rc.w0 == w0 && rc.w1 == w1;
         }
+        ok = ok && found;
       }
-      if (ok) {
-        uint32_t w = 0;
-        for (uint32_t i = 0; i < std::min<uint32_t>(pl - 4, 4); ++i) w |= uint32_t(v.patterns[po + 4 + i]) << (8 * i);
-        ok = w == got && std::memcmp(s.store.data() + po, v.patterns + po, pl) == 0 && in_class(v.patterns + po);
-      }
+      ok = ok && std::memcmp(s.store.data() + po, v.patterns + po, pl) == 0 && in_class(v.patterns + po);
       bad += !ok;
     }
     p += 8 + 16ull * count;
   }
   for (uint32_t i = 0; i < v.n4; ++i) {
     const uint32_t g4v = rd32(v.arr4 + 4ull * i);
-    const Slot *sl = probe(g4v);
+    const Slot *sl = d.key_bytes == 4 ? probe(key_hash(g4v, 0)) : nullptr;
     const uint8_t g4b[4] = {uint8_t(g4v >> 24), uint8_t(g4v >> 16), uint8_t(g4v >> 8), uint8_t(g4v)};
     bad += !(sl && (sl->meta & kSlotShort4) && (d.cls.run == 0 || (d.cls.run == 4 && in_class(g4b))));
   }

@@ -53,8 +53,8 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
 uint64_t check_staged_store(const StoreView &v, const StagedStore &s);
 
 // host mirror of the device hashing (scan.cu uses the same expressions)
-inline uint32_t key_home(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.key_shift; }
-inline uint32_t g4_bit(const DeviceStore &d, uint32_t gram) { return (gram * kHashMul) >> d.g4_shift; }
+inline uint32_t key_home(const DeviceStore &d, uint32_t key) { return key >> d.key_shift; }
+inline uint32_t g4_bit(const DeviceStore &d, uint32_t key) { return key >> d.g4_shift; }
 inline uint32_t p23_bit(const DeviceStore &d, uint32_t gram) {
   return ((gram & d.p23_and) * d.p23_mul) >> d.p23_shift;
 }
