@@ -572,3 +572,45 @@ def test_config5_at_full_size(store_cache):
         assert same_matches(got, want), describe_diff(got, want)
         inside = (off >= lo) & (off + ln <= lo + (2 << 20))
         assert int(inside.sum()) == want.size
+
+
+def _colliding_patterns(k: int):
+    """Two patterns whose first k bytes differ but hash to the same 32-bit key
+    (device_tables.h key_hash: gram * M1 ^ tail * M2, M1 odd hence invertible)."""
+    M1, M2, mask32 = 0x9E3779B1, 0x85EBCA6B, 0xFFFFFFFF
+    inv = pow(M1, -1, 1 << 32)
+    a = b"abcdefgh"[:k] + b"-first"
+    gram_a = int.from_bytes(a[:4], "big")
+    tail_mask = (1 << (8 * (k - 4))) - 1
+    tail_a = int.from_bytes(a[4:8], "little") & tail_mask
+    key = ((gram_a * M1) ^ (tail_a * M2)) & mask32
+    for t in range(1, 1 << 16):
+        tail_b = int.from_bytes(bytes([0x41 + t % 26, 0x61 + (t // 26) % 26, 0x30 + (t // 676) % 10, 0x42][:k - 4]).ljust(4, b"\0"), "little")
+        gram_b = (((key ^ (tail_b * M2)) & mask32) * inv) & mask32
+        head = gram_b.to_bytes(4, "big") + tail_b.to_bytes(4, "little")[:k - 4]
+        if b"\n" in head or b"\r" in head or head == a[:k]:
+            continue
+        b = head + b"-second"
+        assert (((int.from_bytes(b[:4], "big") * M1) ^ ((int.from_bytes(b[4:8], "little") & tail_mask) * M2)) & mask32) == key
+        return a, b
+    raise AssertionError("no collision found")
+
+
+@pytest.mark.parametrize("k", [5, 6, 7, 8])
+def test_key_collisions_between_different_prefixes(store_cache, k):
+    """Keys are 32-bit hashes of the first K pattern bytes: two different prefixes with the same
+    key share a slot and must be told apart by the byte compare."""
+    a, b = _colliding_patterns(k)
+    filler = [bytes([0x61 + i % 26]) * k + b"pad%03d" % i for i in range(40)]  # keeps the shortest pattern at k + ...
+    pats = [a[:k + 1], a, b, b[:k + 2]] + filler
+    pats = [p for p in pats if len(p) >= k]
+    shortest = min(len(p) for p in pats)
+    pats.append(b"q" * k)  # pins K = k
+    path = store_cache(f"collide-{k}", b"\n".join(pats))
+    o = Oracle.from_olm(path)
+    hay = b"..".join([a, b, a[:k] + b"x", b[:k] + b"y", b + a, a[:k + 1], b"q" * (k + 3)] * 50)
+    with Matcher(path) as m:
+        got = check(m, o, hay)
+        check(m, o, hay, longest_only=True)
+        check(m, o, hay, word_boundary=True)
+        assert got.size >= 50 * 8 and shortest >= k

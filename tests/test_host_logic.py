@@ -213,3 +213,20 @@ def test_staging_facts_and_class_prefilter_choice(tmp_path, product_lib):
     assert inspect(wide)["class_run"] == 0  # class too wide to be worth its instructions
     i = inspect(inputs.golden_data("names.txt"))
     assert i["class_run"] == 0 and i["len3"] == 612
+
+
+def test_key_bytes_choice(tmp_path, product_lib):
+    """Keys cover min(shortest pattern, 8) bytes, 4 when the store has 1..4 byte patterns."""
+    def kb(buf):
+        p = tmp_path / f"k{abs(hash(buf)) % 10**9}.olm"
+        Compiler.compile_from_buffer(str(p), buf)
+        info = StoreInfoC()
+        assert product_lib.olm_store_inspect(os.fsencode(p), C.byref(info)) == 0
+        return info.as_dict()["key_bytes"]
+
+    assert kb(b"\n".join(inputs.synth_long_patterns(3000))) == 6
+    assert kb(b"abcde\nabcdefghij\n") == 5
+    assert kb(b"abcdefghijkl\nmnopqrstuvwxyz\n") == 8
+    assert kb(b"abcdefgh\nabcd\n") == 4
+    assert kb(b"abcdefgh\nab\n") == 4
+    assert kb(inputs.golden_data("names.txt")) == 4
