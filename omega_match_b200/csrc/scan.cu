@@ -448,16 +448,36 @@ struct Scanner {
     }
   }
 
-  // class prefilter: bit 7 of every byte of the result = byte is in the class
-  __device__ __forceinline__ uint32_t class_word(uint32_t w) const {
-    const ByteClass &c = P.st.cls;
-    const uint32_t t = w & c.and4;
-    uint32_t in = (t + c.addlo[0]) & ~(t + c.addhi[0]);
-    if (c.n_ranges > 1) in |= (t + c.addlo[1]) & ~(t + c.addhi[1]);
-    return in & ~w & 0x80808080u;
-  }
   // bits 7,15,23,31 -> bits 0..3
   static __device__ __forceinline__ uint32_t gather4(uint32_t m) { return __umulhi(m, 0x02040810u) & 0xFu; }
+
+  // class bits of the 24 haystack bytes a lane holds (bit i = byte i is in the class), then
+  // bit i = bytes i .. i+run-1 are all in the class (run = 4, 5, 6 or 8; i < 16)
+  __device__ __forceinline__ uint32_t class_runs16(const uint4 &v, const uint2 &nx) const {
+    const ByteClass &c = P.st.cls;
+    const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
+    const uint32_t and4 = c.and4, lo0 = c.addlo[0], hi0 = c.addhi[0];
+    uint32_t a = 0;
+    if (c.n_ranges > 1) { // (uniform branch: one block of straight-line code per case)
+      const uint32_t lo1 = c.addlo[1], hi1 = c.addhi[1];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t t = w[i] & and4;
+        const uint32_t in = ((t + lo0) & ~(t + hi0)) | ((t + lo1) & ~(t + hi1));
+        a |= gather4(in & ~w[i] & 0x80808080u) << (4 * i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t t = w[i] & and4;
+        a |= gather4((t + lo0) & ~(t + hi0) & ~w[i] & 0x80808080u) << (4 * i);
+      }
+    }
+    a &= a >> 1;
+    a &= a >> 2;
+    a &= a >> (c.run - 4);
+    return a & 0xFFFFu;
+  }
 
   // stage 1 for one lane: 16 positions -> candidate masks (bit k = position lpos + k)
   __device__ __forceinline__ void stage1(const TileCtx &T, uint32_t lpos, uint32_t &cg, uint32_t &cp) const {
@@ -466,19 +486,7 @@ struct Scanner {
     cg = 0;
     cp = 0;
     if (HAS_CLS) {
-      const uint2 nx = lds64(src + 16);
-      // bit i = byte lpos+i is in the class, i < 24
-      uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
-                   (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
-                   (gather4(class_word(nx.y)) << 20);
-      // bit i = bytes lpos+i .. lpos+i+run-1 are all in the class (run <= 8, i < 16)
-      uint32_t have = 1;
-      while (have * 2 <= P.st.cls.run) {
-        a &= a >> have;
-        have *= 2;
-      }
-      if (have < P.st.cls.run) a &= a >> (P.st.cls.run - have);
-      cg = a & 0xFFFFu;
+      cg = class_runs16(v, lds64(src + 16));
       return;
     }
     const uint2 w45 = lds64(src + 16);
@@ -668,17 +676,7 @@ struct Scanner {
     const uint4 v = lds128(src);
     uint32_t cand = 0, cp = 0; // cp: candidates of the 1..3 byte patterns (HAS_P23)
     if (HAS_CLS) {
-      const uint2 nx = lds64(src + 16);
-      uint32_t a = gather4(class_word(v.x)) | (gather4(class_word(v.y)) << 4) | (gather4(class_word(v.z)) << 8) |
-                   (gather4(class_word(v.w)) << 12) | (gather4(class_word(nx.x)) << 16) |
-                   (gather4(class_word(nx.y)) << 20);
-      uint32_t have = 1;
-      while (have * 2 <= P.st.cls.run) {
-        a &= a >> have;
-        have *= 2;
-      }
-      if (have < P.st.cls.run) a &= a >> (P.st.cls.run - have);
-      cand = a & 0xFFFFu;
+      cand = class_runs16(v, lds64(src + 16));
     } else {
       const uint2 w45 = lds64(src + 16);
       const uint32_t w[6] = {v.x, v.y, v.z, v.w, w45.x, w45.y};
@@ -768,9 +766,10 @@ struct Scanner {
           pass[u] = pass[u] && ((e[u] >> 9) & 1u);
           e[u] &= 511u;
         }
-        const uint32_t a = tile_off + e[u];
-        uint32_t h = __byte_perm(lds_le32(a), 0, 0x0123) * kHashMul;
-        if (tmask) h ^= (lds_le32(a + 4) & tmask) * kHashMul2; // keys longer than 4 bytes
+        const uint32_t a = tile_off + e[u], a4 = a & ~3u, sh8 = a << 3;
+        const uint32_t x0 = lds32(a4), x1 = lds32(a4 + 4); // bytes 0..7 of the position from three aligned words
+        uint32_t h = __byte_perm(__funnelshift_r(x0, x1, sh8), 0, 0x0123) * kHashMul;
+        if (tmask) h ^= (__funnelshift_r(x1, lds32(a4 + 8), sh8) & tmask) * kHashMul2; // keys longer than 4 bytes
         gram[u] = h; // the key of the position
         if (near_end) pass[u] = pass[u] && (e[u] + kbytes <= rem_c); // only the segment's last chunks
         if (HAS_CLS) {
