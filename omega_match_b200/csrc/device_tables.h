@@ -12,8 +12,8 @@
 //             hash to the same key -- ~n^2 / 2^33 pairs -- they then share a slot and are told
 //             apart by the byte compare.)  A key lives in the first bucket, counted from its
 //             home bucket, that had a free place when it was inserted; places fill left to
-//             right, so a bucket whose last place holds `empty_key` ends a probe.  Load <= 0.25:
-//             a probe -- hit or miss -- costs one 16-byte load in ~98% of the cases (role of
+//             right, so a bucket whose last place holds `empty_key` ends a probe.  Load <= 0.125:
+//             a probe -- hit or miss -- costs one 16-byte load in 99.8% of the cases (role of
 //             probe_bucket, hash_table.c:91-109).  `empty_key` is a value that is no key.
 //   slots[]   parallel to keys[] (slot = 4*bucket + place), read only after a key hit: pattern
 //             bytes 0..7 and the length of the (single) pattern, so that a pattern of up to 8

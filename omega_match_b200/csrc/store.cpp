@@ -11,6 +11,13 @@
 
 #include "host_util.h"
 
+// buckets of the key table = 2^OLM_KEY_EXTRA_LOG2 x the smallest power of two >= #keys.  With 1 a
+// probe meets a full bucket (and has to look at the next one) 0.2 % of the time instead of 1.6 %;
+// as a warp takes that path when ANY of its 32 probes does, this is 5 % instead of 40 % of the
+// rounds (measured: +4 % throughput at 1 M patterns; the table -- 32 MiB -- still lives in L2).
+#ifndef OLM_KEY_EXTRA_LOG2
+#define OLM_KEY_EXTRA_LOG2 1
+#endif
 namespace olm {
 
 std::string parse_store(const uint8_t *f, size_t size, StoreView *v) {
@@ -159,8 +166,8 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
   std::sort(all.begin(), all.end());
   all.erase(std::unique(all.begin(), all.end()), all.end());
   const uint64_t n_keys_total = all.size();
-  // buckets of four places; #buckets >= #keys, i.e. load <= 0.25
-  uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, n_keys_total)));
+  // buckets of four places; #buckets >= 2 x #keys, i.e. load <= 0.125
+  uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, n_keys_total)) + OLM_KEY_EXTRA_LOG2);
   if (lg_buckets > 27) return "too many distinct keys";
   const uint32_t n_buckets = 1u << lg_buckets;
   d.key_shift = 32 - lg_buckets;

@@ -187,7 +187,7 @@ def test_torch_generators_equal_numpy():
 
 
 def test_staging_facts_and_class_prefilter_choice(tmp_path, product_lib):
-    """What store.cpp derives for the GPU: key table at load <= 0.25, gram bitmap, and the
+    """What store.cpp derives for the GPU: key table at load <= 0.125, gram bitmap, and the
     byte-class prefilter only where it is sound (no 1..3 byte patterns, 7-bit leading bytes,
     a class that excludes most byte values)."""
     def inspect(buf, flags=(0, 0, 0)):
@@ -200,7 +200,7 @@ def test_staging_facts_and_class_prefilter_choice(tmp_path, product_lib):
     i = inspect(b"\n".join(inputs.synth_long_patterns(5000)))  # a-zA-Z, length 6..24
     assert (i["class_run"], i["class_and_mask"], i["class_ranges"]) == (6, 0x5F, 1)
     assert (i["class_lo"][0], i["class_hi"][0]) == (0x41, 0x5A)
-    assert i["gram_keys"] <= i["key_buckets"] < 2 * max(8, i["gram_keys"]) and i["g4_bits"] >= 16 * i["gram_keys"]
+    assert 2 * i["gram_keys"] <= i["key_buckets"] < 4 * max(8, i["gram_keys"]) and i["g4_bits"] >= 16 * i["gram_keys"]
     i = inspect(b"0123456\n9876543210\n55555\n")  # digits, shortest 5
     assert (i["class_run"], i["class_and_mask"], i["class_ranges"], i["class_lo"][0], i["class_hi"][0]) == (5, 0x7F, 1, 0x30, 0x39)
     i = inspect(b"deadbeef01\ncafe0123\n")  # two ranges: 0-9, a-f
