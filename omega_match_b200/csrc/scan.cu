@@ -786,8 +786,11 @@ struct Scanner {
         if (u > 0 && base + u * 32 >= total) break;
         const uint32_t g = gram[u];
         bool hit = HAS_G4 && pass[u] && (kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g);
-        // rare: the home bucket is full and does not hold the gram -> next bucket(s)
-        if (HAS_G4 && __any_sync(kFull, pass[u] && !hit && kb[u].w != empty)) {
+        // rare: the home bucket is full and does not hold the key -> next bucket(s)
+        const bool more = HAS_G4 && pass[u] && !hit && kb[u].w != empty;
+        // at 1 M patterns nearly every round ends here: no key hit, no full bucket -- one vote
+        if (!__any_sync(kFull, hit || more || (HAS_P23 && shortc[u]))) continue;
+        if (HAS_G4 && __any_sync(kFull, more)) {
           while (pass[u] && !hit && kb[u].w != empty) {
             bucket[u] = (bucket[u] + 1) & P.st.key_mask;
             kb[u] = __ldg(keys + bucket[u]);
