@@ -204,6 +204,15 @@ int olm_cuda_sort_records(const omega_list_matcher_t *matcher, void *dev_records
 
 int olm_cuda_last_timing(const omega_list_matcher_t *matcher, olm_cuda_timing_t *out);
 
+/* Statistics (omega_match_stats_t, list_matcher.h:43-49, filled as matcher.c:783-799, :818-877,
+ * :210 do).  Default: the counters the scan produces by itself -- hits, misses and comparisons of
+ * ITS tables, attempts, filtered = attempts - hits -- at no cost.  With exact statistics on, every
+ * match call of a matcher that has a stats struct attached also runs one kernel that evaluates
+ * the reference's 3-probe Bloom filter (bloom.c:51-64) and gram -> bucket map
+ * (hash_table.c:91-109) for every position, and the five counters equal the reference's.
+ * Also switched on for all matchers by the environment variable OLM_EXACT_STATS=1. */
+int olm_cuda_set_exact_stats(omega_list_matcher_t *matcher, int on);
+
 /* Pinned host memory helpers (so callers can hand DMA-able buffers to _match). */
 void *olm_cuda_host_alloc(size_t bytes);
 void olm_cuda_host_free(void *p);

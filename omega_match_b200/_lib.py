@@ -100,6 +100,7 @@ ABI = [
     ("olm_cuda_no_overlap", C.c_int64, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_sort_records", _ci, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_last_timing", _ci, [_vp, C.POINTER(CudaTimingC)]),
+    ("olm_cuda_set_exact_stats", _ci, [_vp, _ci]),
     ("olm_cuda_host_alloc", _vp, [C.c_size_t]),
     ("olm_cuda_host_free", None, [_vp]),
     ("olm_store_inspect", _ci, [_cp, C.POINTER(StoreInfoC)]),

@@ -23,6 +23,7 @@ struct omega_list_matcher_struct {
   size_t file_size = 0;
   char *temp_path = nullptr; // set when the store was compiled on the fly (matcher.c:458-481)
   omega_match_stats_t *stats = nullptr;
+  bool exact_stats = false; // olm_cuda_set_exact_stats / OLM_EXACT_STATS=1
   int threads = 1;
   int chunk = 4096;
 };
@@ -118,6 +119,9 @@ omega_list_matcher_t *omega_list_matcher_create_from_buffer(const char *compiled
 int omega_list_matcher_add_stats(omega_list_matcher_t *m, omega_match_stats_t *stats) {
   if (!m || !stats) return -1;
   m->stats = stats;
+  const char *ex = std::getenv("OLM_EXACT_STATS");
+  if (ex && ex[0] == '1') m->exact_stats = true;
+  m->engine->set_exact_stats(m->exact_stats);
   return 0;
 }
 
@@ -242,6 +246,13 @@ int64_t olm_cuda_no_overlap(const omega_list_matcher_t *m, void *dev_records, ui
 int olm_cuda_sort_records(const omega_list_matcher_t *m, void *dev_records, uint64_t count) {
   if (!m || !m->engine) return -1;
   return m->engine->sort_records(dev_records, count);
+}
+
+int olm_cuda_set_exact_stats(omega_list_matcher_t *m, int on) {
+  if (!m || !m->engine) return -1;
+  m->exact_stats = on != 0;
+  m->engine->set_exact_stats(m->exact_stats && m->stats); // the kernel runs only for an attached struct
+  return 0;
 }
 
 int olm_cuda_last_timing(const omega_list_matcher_t *m, olm_cuda_timing_t *out) {

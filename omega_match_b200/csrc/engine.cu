@@ -25,6 +25,7 @@
 
 #include "filters.cuh"
 #include "scan.cuh"
+#include "stats.cuh"
 #include "transform.cuh"
 
 namespace olm {
@@ -102,6 +103,12 @@ struct EngineImpl {
   uint64_t out_hint = 0;
   unsigned long long counters[8] = {};
   uint64_t attempts_last = 0;
+  // exact statistics (stats.cuh): tables uploaded at create(), the kernel runs only while a stats
+  // struct is attached to the matcher
+  DevBuf d_bloom, d_smap, d_slens;
+  StatsTables stats;
+  bool want_stats = false, stats_valid = false;
+  unsigned long long stat_counters[5] = {};
 };
 
 Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string *err) {
@@ -152,6 +159,21 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && upload(impl->d_p23, staged.p23, &impl->ds.p23) == 0;
   ok = ok && upload(impl->d_set3, staged.set3, &impl->ds.set3) == 0;
   ok = ok && upload(impl->d_bitmap2, staged.bitmap2, &impl->ds.bitmap2) == 0;
+  {
+    StagedStats ss;
+    e = stage_stats(view, &ss);
+    if (!e.empty()) {
+      delete eng;
+      return fail(e);
+    }
+    impl->stats.bloom_mask = ss.bloom_mask;
+    impl->stats.map_shift = ss.map_shift;
+    impl->stats.map_mask = ss.map_mask;
+    impl->stats.largest = view.hdr.largest;
+    ok = ok && upload(impl->d_bloom, ss.bloom, &impl->stats.bloom) == 0;
+    ok = ok && upload(impl->d_smap, ss.map, &impl->stats.map) == 0;
+    ok = ok && upload(impl->d_slens, ss.lens, &impl->stats.lens) == 0;
+  }
   ok = ok && cudaStreamCreateWithFlags(&impl->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&impl->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
@@ -176,7 +198,8 @@ Engine::~Engine() {
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
                     &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->misc,
-                    &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch})
+                    &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
+                    &impl_->d_slens})
     b->release();
   for (auto &ev : impl_->ev)
     if (ev) cudaEventDestroy(ev);
@@ -242,6 +265,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   unsigned long long *d_ftotal = d_total + 1;
   unsigned long long *d_counters = d_total + 2;
   unsigned long long *d_temp_count = d_total + 10;
+  unsigned long long *d_stats = d_total + 11; // five counters of stats_kernel (the memset below clears 16 words)
+  E.stats_valid = false;
 
   const bool identity_map = windowed && !(E.hdr.flags & (kFlagIgnorePunct | kFlagElideSpace));
   if (windowed) {
@@ -264,6 +289,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   if (f.longest_only) fl |= kLongestOnly;
   if (windowed) fl |= kWindowMode;
   if (identity_map) fl |= kIdentityMap;
+  if (E.want_stats) fl |= kCountAll;
 
   unsigned long long total = 0, temp_used = 0;
   uint64_t temp_extra = 0; // grows when the block allocator of temp[] wasted more than the slack
@@ -315,6 +341,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
           OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[need], 0));
         }
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
+        if (E.want_stats) OLM_CUDA(stats_launch(P, E.stats, d_stats, E.sms, E.stream, &launches));
         ++scan_launches;
       }
     } else {
@@ -351,10 +378,13 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.ticket = d_tickets + b;
         P.redo_flag = d_redo_flags + b;
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
+        if (E.want_stats) OLM_CUDA(stats_launch(P, E.stats, d_stats, E.sms, E.stream, &launches));
         ++scan_launches;
       }
     }
     OLM_CUDA(cudaEventRecord(E.ev[1], E.stream));
+    if (E.want_stats)
+      OLM_CUDA(cudaMemcpyAsync(E.stat_counters, d_stats, sizeof E.stat_counters, cudaMemcpyDeviceToHost, E.stream));
     OLM_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, E.stream));
     OLM_CUDA(cudaMemcpyAsync(&temp_used, d_temp_count, sizeof temp_used, cudaMemcpyDeviceToHost, E.stream));
     OLM_CUDA(cudaMemcpyAsync(E.counters, d_counters, sizeof E.counters, cudaMemcpyDeviceToHost, E.stream));
@@ -370,6 +400,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     if (total > cap) cap = total + total / 16 + 4096; // exact count is known now
   }
   E.out_hint = std::max<uint64_t>(E.out_hint, total + total / 8);
+  E.stats_valid = E.want_stats;
   E.last.matches_before_filter = total;
   float ms = 0.f;
   cudaEventElapsedTime(&ms, E.ev[0], E.ev[1]);
@@ -517,10 +548,23 @@ int Engine::sort_records(void *dev_records, uint64_t count) {
   return 0;
 }
 
+void Engine::set_exact_stats(bool on) { impl_->want_stats = on; }
+
 void Engine::collect_stats(omega_match_stats_t *s) {
   if (!s) return;
   const EngineImpl &E = *impl_;
-  // counters written by the scan: [0] hits  [1] misses  [2] comparisons
+  // counters written by the scan: [0] hits (key slots found + short matches accepted)
+  // [1] misses (short candidates rejected by a predicate)  [2] comparisons  [3] key slots found
+  if (E.stats_valid) {
+    // exact (stats.cuh): the long path as core_match() counts it (matcher.c:783-799, :210),
+    // the short matcher's hits and misses (:818-877) from the scan
+    s->total_attempts += E.stat_counters[kStatAttempts];
+    s->total_filtered += E.stat_counters[kStatFiltered];
+    s->total_misses += E.stat_counters[kStatLongMisses] + E.counters[1];
+    s->total_hits += E.stat_counters[kStatLongHits] + (E.counters[0] - E.counters[3]);
+    s->total_comparisons += E.stat_counters[kStatComparisons];
+    return;
+  }
   s->total_hits += E.counters[0];
   s->total_misses += E.counters[1];
   s->total_comparisons += E.counters[2];

@@ -51,6 +51,9 @@ public:
 
   const olm_cuda_timing_t &timing() const;
   void collect_stats(omega_match_stats_t *accum); // adds the counters of the last call
+  // While on, every call also runs stats_kernel (stats.cuh) so that collect_stats() reports the
+  // reference's counters exactly; off (default): the scan's own counters, no extra kernel.
+  void set_exact_stats(bool on);
 
 private:
   Engine() = default;

@@ -281,7 +281,7 @@ struct Scanner {
   //               `emit(len)` is called once per accepted match, longest first.
   static constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
   struct Probe {
-    uint32_t tpos, gram, bucket, flags; // gram: the position's key; flags: 1 = alive, 2 = key candidate (enough bytes left), 4 = short candidate
+    uint32_t tpos, gram, bucket, flags; // gram: the position's key; flags: 1 = alive, 2 = key candidate (enough bytes left), 4 = short candidate, 8 = a start predicate failed (exact statistics only)
     uint4 kb;
   };
 
@@ -292,6 +292,7 @@ struct Scanner {
     pr.gram = 0;
     pr.bucket = 0;
     pr.kb = make_uint4(0, 0, 0, 0);
+    uint32_t bad_start = 0;
     if (!valid) return;
     const uint32_t q = T.sb32 + kTilePre + tpos;
     if (fl & (kWordBoundary | kWordPrefix | kLineStart)) {
@@ -302,11 +303,17 @@ struct Scanner {
         const bool pw = at0 ? false : is_word_byte(prev);
         if (cw == pw) return;
       }
-      if ((fl & kWordPrefix) && !at0 && is_word_byte(prev)) return;     // :195, :806
-      if ((fl & kLineStart) && !at0 && !is_line_end_byte(prev)) return; // :196, :807
+      bool bad = (fl & kWordPrefix) && !at0 && is_word_byte(prev);       // :195, :806
+      bad = bad || ((fl & kLineStart) && !at0 && !is_line_end_byte(prev)); // :196, :807
+      if (bad) {
+        // nothing can match here.  Exact statistics: a short-matcher candidate still has to be looked
+        // up, because the reference counts it as a miss (matcher.c:818-877)
+        if (!((fl & kCountAll) && (cand_p || (cand_g && P.st.n4)))) return;
+        bad_start = 8u;
+      }
     }
     const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
-    pr.flags = 1u | (cand_p ? 4u : 0u);
+    pr.flags = 1u | (cand_p ? 4u : 0u) | bad_start;
     if (HAS_G4 && cand_g && T.rem0 - tpos >= P.st.key_bytes) {
       const uint32_t h = key_hash(gram, P.st.tail_mask ? lds_le32(q + 4) & P.st.tail_mask : 0u);
       pr.gram = h; // the key of the position
@@ -343,16 +350,23 @@ struct Scanner {
   }
 
   template <typename Emit>
-  __device__ __forceinline__ void verify(const TileCtx &T, uint32_t tpos, uint32_t slot, bool cand_p, Emit &&emit) const {
+  __device__ __forceinline__ void verify(const TileCtx &T, uint32_t tpos, uint32_t slot, bool cand_p, bool bad_start,
+                                         Emit &&emit) const {
     const uint32_t rem = T.rem0 - tpos;
     const uint32_t q = T.sb32 + kTilePre + tpos;
     bool emitted = false;
     const bool longest = fl & kLongestOnly;
+    // exact statistics: the reference counts the short matcher's hits and misses before its
+    // longest filter runs (matcher.c:818-877 vs :611), so what `longest` lets this kernel skip
+    // is still evaluated -- and counted -- but not emitted
+    const bool count_all = fl & kCountAll;
 
     if (HAS_G4 && slot != kNoSlot) {
       const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + slot));
       const uint32_t meta = s.z; // 0 when the gram equals empty_key and matched an unused place
-      if (meta != 0) {
+      if (meta != 0 && bad_start) { // exact statistics: only the 4-byte set is looked at
+        if (meta & kSlotShort4) n_miss += stat_inc;
+      } else if (meta != 0) {
         const unsigned long long hay = ((unsigned long long)lds_le32(q + 4) << 32) | lds_le32(q);
         if (meta & kSlotValueMask) {
           n_hits += stat_inc;
@@ -388,9 +402,9 @@ struct Scanner {
             }
           }
         }
-        if ((meta & kSlotShort4) && !(longest && emitted)) {
+        if ((meta & kSlotShort4) && (count_all || !(longest && emitted))) {
           if (end_ok_short(T, tpos, 4)) {
-            emit(4u);
+            if (!(longest && emitted)) emit(4u);
             emitted = true;
             n_hits += stat_inc;
           } else {
@@ -399,7 +413,7 @@ struct Scanner {
         }
       }
     }
-    if (HAS_P23 && cand_p && !(longest && emitted)) {
+    if (HAS_P23 && cand_p && (count_all || !(longest && emitted))) {
       const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
       if (P.st.n3 && rem >= 3) {
         const uint32_t k3 = gram >> 8;
@@ -413,8 +427,8 @@ struct Scanner {
           }
         }
         if (hit) {
-          if (end_ok_short(T, tpos, 3)) {
-            emit(3u);
+          if (!bad_start && end_ok_short(T, tpos, 3)) {
+            if (!(longest && emitted)) emit(3u);
             emitted = true;
             n_hits += stat_inc;
           } else {
@@ -422,11 +436,11 @@ struct Scanner {
           }
         }
       }
-      if (P.st.n2 && rem >= 2 && !(longest && emitted)) {
+      if (P.st.n2 && rem >= 2 && (count_all || !(longest && emitted))) {
         const uint32_t k2 = gram >> 16;
         if ((__ldg(P.st.bitmap2 + (k2 >> 5)) >> (k2 & 31)) & 1u) {
-          if (end_ok_short(T, tpos, 2)) {
-            emit(2u);
+          if (!bad_start && end_ok_short(T, tpos, 2)) {
+            if (!(longest && emitted)) emit(2u);
             emitted = true;
             n_hits += stat_inc;
           } else {
@@ -434,11 +448,11 @@ struct Scanner {
           }
         }
       }
-      if (P.st.n1 && !(longest && emitted)) {
+      if (P.st.n1 && (count_all || !(longest && emitted))) {
         const uint32_t k1 = gram >> 24;
         if ((P.st.bitmap1[k1 >> 5] >> (k1 & 31)) & 1u) {
-          if (end_ok_short(T, tpos, 1)) {
-            emit(1u);
+          if (!bad_start && end_ok_short(T, tpos, 1)) {
+            if (!(longest && emitted)) emit(1u);
             n_hits += stat_inc;
           } else {
             n_miss += stat_inc;
@@ -525,7 +539,7 @@ struct Scanner {
     const unsigned long long ent = mine ? lds64u(q2 + 8u * lane) : 0ull; // q2, stage: shared-space addresses
     const uint32_t slot = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
     const uint32_t tpos = hi & 0xFFFFu;
-    const bool cand_p = (hi >> 16) & 1u;
+    const bool cand_p = (hi >> 16) & 1u, bad_start = (hi >> 17) & 1u;
     // One copy of verify() in the instruction stream: positions with more than four matches are
     // evaluated again (skip = 4, 8, ...) by the same code -- rare, and the kernel is I-cache bound.
     uint32_t at = 0, tot = 0, skip = 0;
@@ -534,7 +548,7 @@ struct Scanner {
     do {
       uint32_t cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
       if (mine)
-        verify(T, tpos, slot, cand_p, [&](uint32_t len) {
+        verify(T, tpos, slot, cand_p, bad_start, [&](uint32_t len) {
           const uint32_t j = cnt - skip; // wraps to a huge value while cnt < skip
           if (j == 0) m0 = len;
           else if (j == 1) m1 = len;
@@ -636,7 +650,7 @@ struct Scanner {
         const uint32_t bal = __ballot_sync(kFull, want);
         if (want)
           sts64u(q2 + 8u * (q2n + __popc(bal & lt)),
-                 ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 4u) << 14)) << 32) | slot);
+                 ((unsigned long long)(pr[u].tpos | ((pr[u].flags & 12u) << 14)) << 32) | slot);
         q2n += __popc(bal);
       }
       __syncwarp();

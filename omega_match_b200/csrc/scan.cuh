@@ -35,6 +35,7 @@ enum ScanFlags : uint32_t {
   kLongestOnly = 1u << 5,
   kWindowMode = 1u << 6,  // segments are normalised 4 MiB windows described by `windows`
   kIdentityMap = 1u << 7, // window mode without an offset map (case folding only)
+  kCountAll = 1u << 8,    // exact statistics: count the short candidates kLongestOnly skips (stats.cuh)
 };
 
 // Geometry of the kernel (compile-time; DESIGN.md "scan kernel").

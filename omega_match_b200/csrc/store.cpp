@@ -397,6 +397,38 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
   return "";
 }
 
+std::string stage_stats(const StoreView &v, StagedStats *s) {
+  *s = StagedStats{};
+  const Header &h = v.hdr;
+  if (v.bloom_bits == 0 || (v.bloom_bits & (v.bloom_bits - 1)) || uint64_t(v.bloom_bits) / 8 > h.bloom_bytes)
+    return "bloom filter size is not a power of two that fits its section";
+  s->bloom.assign(std::max<size_t>(1, v.bloom_bits / 64), 0);
+  std::memcpy(s->bloom.data(), v.bloom, std::min<size_t>(s->bloom.size() * 8, h.bloom_bytes));
+  s->bloom_mask = v.bloom_bits - 1;
+  const uint32_t lg = std::max<uint32_t>(4, ceil_log2(std::max<uint64_t>(1, h.occupied) * 2));
+  if (lg > 30) return "too many buckets";
+  s->map.assign(size_t(1) << lg, make_uint2(0, 0));
+  s->map_shift = 32 - lg;
+  s->map_mask = (1u << lg) - 1;
+  for (uint64_t p = 0; p < h.blob_bytes;) { // (validated by stage_store)
+    if (p + 8 > h.blob_bytes) return "truncated bucket header";
+    const uint32_t gram = rd32(v.blob + p), count = rd32(v.blob + p + 4);
+    if (count == 0 || p + 8 + uint64_t(count) * kBucketRecordBytes > h.blob_bytes) return "bucket runs past the bucket data";
+    if (s->lens.size() + count + 1 >= 0xFFFFFFF0ull) return "too many patterns";
+    const uint32_t at = uint32_t(s->lens.size());
+    s->lens.push_back(count);
+    for (uint32_t j = 0; j < count; ++j) s->lens.push_back(rd32(v.blob + p + 8 + 16ull * j + 8));
+    for (uint32_t i = (gram * kHashMul) >> s->map_shift;; i = (i + 1) & s->map_mask)
+      if (s->map[i].y == 0) {
+        s->map[i] = make_uint2(gram, at + 1);
+        break;
+      }
+    p += 8 + uint64_t(count) * kBucketRecordBytes;
+  }
+  if (s->lens.empty()) s->lens.push_back(0);
+  return "";
+}
+
 uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
   const DeviceStore &d = s.params;
   uint64_t bad = 0;

@@ -47,6 +47,17 @@ struct FilterBudget {
 
 std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedStore *out);
 
+// Host image of the tables behind the exact statistics (stats.cuh): the file's Bloom bits as
+// 64-bit words, its gram -> bucket map as an open-addressing table, the pattern lengths per bucket.
+struct StagedStats {
+  std::vector<unsigned long long> bloom;
+  uint32_t bloom_mask = 0;
+  std::vector<uint2> map; // {gram, 1 + index into lens} or {0, 0}
+  uint32_t map_shift = 32, map_mask = 0;
+  std::vector<uint32_t> lens; // per bucket: count, lengths (file order: longest first)
+};
+std::string stage_stats(const StoreView &v, StagedStats *out);
+
 // Walks every pattern of the file through the staged tables exactly as the scan kernel would
 // probe them; returns the number of patterns that are NOT reachable (0 = tables are sound).
 // Used by CPU-only tests; it does not match haystacks.

@@ -184,6 +184,12 @@ class Matcher:
     def get_match_stats(self) -> MatchStats:
         return MatchStats(**{k: int(getattr(self._match_stats, k)) for k in MatchStats.__annotations__})
 
+    def set_exact_stats(self, on: bool = True) -> None:
+        """B200 extension: make get_match_stats() equal the reference's counters exactly (one extra
+        kernel per call, include/olm_b200.h olm_cuda_set_exact_stats)."""
+        if self._lib.olm_cuda_set_exact_stats(self._matcher, int(bool(on))) != 0:
+            raise RuntimeError("Failed to switch exact statistics")
+
     def reset_match_stats(self) -> None:
         for k in MatchStats.__annotations__:
             setattr(self._match_stats, k, 0)

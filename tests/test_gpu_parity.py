@@ -212,6 +212,40 @@ def test_binding_compile_and_match(tmp_path):
         assert m2.get_match_stats() == MatchStats(0, 0, 0, 0, 0)
 
 
+@pytest.mark.parametrize("sf", [(0, 0, 0), (1, 0, 0), (1, 1, 1)])
+def test_exact_stats_equal_the_reference_counters(store_cache, sf):
+    """omega_match_stats_t (list_matcher.h:43-49; matcher.c:783-799, :818-877, :210, accumulated
+    :887-893): with olm_cuda_set_exact_stats() all five counters equal the oracle's -- which
+    tests/ref_fuzz_worker.py pins on the reference's -- for long + short pattern sets, with and
+    without word_boundary, across 4 MiB windows, and accumulate over calls."""
+    names = [p for p in inputs.golden_data("names.txt").split(b"\n") if p][:6000]
+    pats = names + inputs.synth_long_patterns(3000) + [b"ab", b"the", b"King", b"x", b"of ", b"e\n"]
+    path = store_cache("stats-mixed", b"\n".join(pats), sf)
+    long_only = store_cache("stats-long", b"\n".join(inputs.synth_long_patterns(20000)), sf)
+    hay = inputs.plant(inputs.text_haystack((9 << 20) + 12345, 11), pats, 0x51)
+    for store in (path, long_only):
+        o = Oracle.from_olm(store)
+        with Matcher(store) as m:
+            m.set_exact_stats(True)
+            for flags in ({}, {"word_boundary": True}, {"longest_only": True, "no_overlap": True},
+                          {"word_prefix": True, "line_end": True}):
+                for h in (hay, hay[:70001], hay[:3], b""):
+                    got = m.match_arrays(h, **flags)
+                    want = o.match(h, **flags)
+                    assert same_matches(got, want), describe_diff(got, want)
+                    st = m.get_match_stats()
+                    ref = o.stats.as_dict()
+                    assert (st.total_hits, st.total_misses, st.total_filtered, st.total_attempts,
+                            st.total_comparisons) == (ref["hits"], ref["misses"], ref["filtered"], ref["attempts"],
+                                                      ref["comparisons"]), (store == path, flags, len(h), st, ref)
+            # default mode again: no extra kernel, the scan's own counters
+            m.match_arrays(hay[:70001])
+            on = m.last_timing()["kernel_launches"]
+            m.set_exact_stats(False)
+            m.match_arrays(hay[:70001])
+            assert m.last_timing()["kernel_launches"] == on - 1
+
+
 def test_binding_flags(tmp_path):
     """test_omega_match.py:107-196, :242-325 (case, punctuation, overlap, word and line options)."""
     pat_file = tmp_path / "p.txt"
