@@ -41,20 +41,26 @@ enum ScanFlags : uint32_t {
 // Geometry of the kernel (compile-time; DESIGN.md "scan kernel").
 constexpr int kScanWarps = 31;                      // warps that scan
 constexpr int kScanThreads = 1024;                  // + producer warp (31: tickets, TMA)
-constexpr int kTileBytes = 8192;                    // positions per tile
+#ifndef OLM_TILE_BYTES
+#define OLM_TILE_BYTES 4096
+#endif
+#ifndef OLM_MAX_STAGES
+#define OLM_MAX_STAGES 16
+#endif
+constexpr int kTileBytes = OLM_TILE_BYTES;          // positions per tile
 constexpr int kTilePre = 16;                        // bytes staged in front of a tile (previous byte)
 constexpr int kTileHalo = 112;                      // bytes staged behind a tile
 constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 8320 = 65*128
 constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes: the unit a warp grabs
 constexpr int kTileChunks = kTileBytes / kChunkBytes; // 16
-constexpr int kMaxStages = 8;                       // ring of tile buffers (2, 4 or 8)
-constexpr int kInfoRing = 16;                       // tile descriptions in shared memory (>= 2 * kMaxStages)
+constexpr int kMaxStages = OLM_MAX_STAGES;          // ring of tile buffers (a power of two >= 2)
+constexpr int kInfoRing = 2 * kMaxStages;           // tile descriptions in shared memory (>= 2 * kMaxStages)
 constexpr uint32_t kChunkCapMin = 32;               // staged matches per chunk: at least ...
 constexpr uint32_t kChunkCapMax = 1024;             // ... at most
 constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
 constexpr int kQ2Entries = 96;                      // hit queue per warp (u64 entries): 31 left over + 2 x 32 new
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
-constexpr int kSmemHeader = 2048;                   // barriers, stage infos
+constexpr int kSmemHeader = kMaxStages > 8 ? 4096 : 2048; // barriers, stage infos
 constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
 constexpr uint32_t kChunkOverflow = 0x80000000u;    // ChunkDesc::count flag: records are written by redo_kernel
 constexpr uint32_t kPrefixSpan = 4096;              // chunks per block of the prefix / place kernels
