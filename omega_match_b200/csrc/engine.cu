@@ -140,7 +140,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   StagedStore staged;
   FilterBudget budget;
   const bool has_p23 = view.n1 || view.n2 || view.n3;
-  budget.g4_max_log2 = has_p23 ? 19 : 20;
+  budget.g4_max_log2 = has_p23 ? 19 : OLM_G4_MAX_LOG2;
   budget.p23_max_log2 = 18;
   e = stage_store(view, budget, &staged);
   if (e.empty() && check_staged_store(view, staged) != 0) e = "internal error: staged store failed its self check";

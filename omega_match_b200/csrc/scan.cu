@@ -69,7 +69,7 @@ struct StageInfo { // written by the producer lane, read by everyone after the m
   uint32_t win;
   uint32_t staged;         // bytes valid behind p0 in the stage buffer
   uint32_t seq;            // tile iteration of the CTA this entry describes (written first)
-  uint32_t _pad;
+  uint32_t stage_par;      // stage of the ring that holds the tile | parity of its mbarrier phase << 16
 };
 static_assert(sizeof(StageInfo) == 64, "StageInfo is 64 bytes");
 
@@ -992,10 +992,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     if (lane != 0) return;
     // Tile iteration k of this CTA -> stage k % S.  `seq` is stored first so that a scanning
     // warp can tell that the stage's mbarrier is in ITS generation before it waits on it.
+    // (the ring depth S is any number >= 2: stage and phase parity of an iteration are counted
+    // here and handed to the scanning warps through the tile description)
+    uint32_t ps = 0, ppar = 0;
     auto produce = [&](uint32_t k) {
-      const uint32_t s = k % S;
+      const uint32_t s = ps, par = ppar;
+      if (++ps == S) {
+        ps = 0;
+        ppar ^= 1u;
+      }
       const uint32_t t = atomicAdd(P.ticket, 1u);
       StageInfo &I = H.info[k % kInfoRing];
+      I.stage_par = s | (par << 16);
       if (t >= P.num_tiles) {
         I.tile = kNoTile;
         __threadfence_block();
@@ -1049,7 +1057,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(ctr32) : "memory");
     c = __shfl_sync(kFull, c, 0);
     const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
-    const uint32_t s = k & (S - 1), gen = k >> (31 - __clz(S)); // S is 2, 4 or 8
     const uint32_t I32 = info32 + (k % kInfoRing) * (uint32_t)sizeof(StageInfo);
     // The mbarrier only tells two phases apart: make sure the stage is in OUR generation first.
     // (Chunks past the CTA's last tile may belong to an iteration that is never produced.)
@@ -1062,7 +1069,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       __nanosleep(32);
     }
     if (over) break;
-    mbar_wait32(full32 + 8u * s, gen & 1u);
+    const uint32_t sp = lds32(I32 + (uint32_t)offsetof(StageInfo, stage_par));
+    const uint32_t s = sp & 0xFFFFu;
+    mbar_wait32(full32 + 8u * s, sp >> 16);
     const uint32_t tile = lds32(I32 + (uint32_t)offsetof(StageInfo, tile));
     if (tile == kNoTile) break;
     TileCtx T;
@@ -1342,9 +1351,10 @@ size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_ca
 
 ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
   ScanGeometry g;
-  // the ring depth is a power of two (indexed by mask); whatever shared memory is left goes to
-  // the warps' staging areas (denser matches before a chunk has to be redone)
-  for (uint32_t s = kMaxStages; s >= 2; s >>= 1) {
+  // the deepest ring that fits (refills track the warps more closely the more stages there are);
+  // whatever shared memory is left goes to the warps' staging areas (denser matches before a
+  // chunk has to be redone)
+  for (uint32_t s = kMaxStages; s >= 2; --s) {
     if (scan_smem_bytes(st, s, kChunkCapMin) > smem_limit) continue;
     const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
     uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;

@@ -60,7 +60,7 @@ constexpr uint32_t kChunkCapMax = 1024;             // ... at most
 constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
 constexpr int kQ2Entries = 96;                      // hit queue per warp (u64 entries): 31 left over + 2 x 32 new
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
-constexpr int kSmemHeader = kMaxStages > 8 ? 4096 : 2048; // barriers, stage infos
+constexpr int kSmemHeader = 16 * kMaxStages + 64 * kInfoRing + 256; // barriers, counters, stage infos (a multiple of 128)
 constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
 constexpr uint32_t kChunkOverflow = 0x80000000u;    // ChunkDesc::count flag: records are written by redo_kernel
 constexpr uint32_t kPrefixSpan = 4096;              // chunks per block of the prefix / place kernels

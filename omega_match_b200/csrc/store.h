@@ -41,7 +41,10 @@ struct StagedStore {
 
 // Limits for the two shared-memory filters, in log2(bits).
 struct FilterBudget {
-  uint32_t g4_max_log2 = 20;  // 128 KiB
+#ifndef OLM_G4_MAX_LOG2
+#define OLM_G4_MAX_LOG2 20
+#endif
+  uint32_t g4_max_log2 = OLM_G4_MAX_LOG2;  // 128 KiB
   uint32_t p23_max_log2 = 18; // 32 KiB
 };
 
