@@ -56,6 +56,9 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 #define OLM_FAST_UNROLL 2
 #endif
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+#ifndef OLM_CLS_SKIP_BITMAP
+#define OLM_CLS_SKIP_BITMAP 0
+#endif
 
 struct StageInfo { // written by the producer lane, read by everyone after the mbarrier wait
   unsigned long long p0;   // segment-relative position of the tile's first byte
@@ -127,6 +130,25 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // Shared memory by 32-bit shared-space address.  The scanning warps never dereference a generic
 // pointer into shared memory: every generic access makes nvcc recompute the shared window base
 // (S2R SR_CgaCtaId + LEA, on the slow XU pipe) -- ~35 of them per chunk saturated that pipe.
+// one bucket of the key table.  (Variants measured at 1 M patterns)
+#ifndef OLM_KEY_LOAD
+#define OLM_KEY_LOAD 1
+#endif
+__device__ __forceinline__ uint4 ld_keys(const uint4 *p) {
+#if OLM_KEY_LOAD == 0
+  return __ldg(p);
+#else
+  uint4 v;
+#if OLM_KEY_LOAD == 1
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#elif OLM_KEY_LOAD == 2
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
+  asm volatile("ld.global.nc.L1::evict_first.L2::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
+  return v;
+#endif
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -786,13 +808,13 @@ struct Scanner {
         if (tmask) h ^= (__funnelshift_r(x1, lds32(a4 + 8), sh8) & tmask) * kHashMul2; // keys longer than 4 bytes
         gram[u] = h; // the key of the position
         if (near_end) pass[u] = pass[u] && (e[u] + kbytes <= rem_c); // only the segment's last chunks
-        if (HAS_CLS) {
+        if (HAS_CLS && !OLM_CLS_SKIP_BITMAP) {
           const uint32_t b = h >> g4_shift;
           const uint32_t word = lds32(g4_off + ((b >> 5) << 2));
           pass[u] = pass[u] && ((word >> (b & 31)) & 1u);
         }
         bucket[u] = h >> key_shift;
-        if (HAS_G4 && pass[u]) kb[u] = __ldg(keys + bucket[u]); // (not read when !pass[u])
+        if (HAS_G4 && pass[u]) kb[u] = ld_keys(keys + bucket[u]); // (not read when !pass[u])
       }
       static_assert(U == 2, "Q2 holds 31 + 2 x 32 entries");
 #pragma unroll
@@ -807,7 +829,7 @@ struct Scanner {
         if (HAS_G4 && __any_sync(kFull, more)) {
           while (pass[u] && !hit && kb[u].w != empty) {
             bucket[u] = (bucket[u] + 1) & P.st.key_mask;
-            kb[u] = __ldg(keys + bucket[u]);
+            kb[u] = ld_keys(keys + bucket[u]);
             hit = kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g;
           }
         }
