@@ -64,6 +64,37 @@ def test_reference_cli_goldens(store_cache, pats, hay, flags, expected):
         assert same_matches(got, want), describe_diff(got, want)
 
 
+# ---- the reference's own CLI, relinked against the product ----
+
+CLI = inputs.GOLDEN.parent.parent / "oracle" / "_ref" / "olm_b200"
+
+
+@pytest.mark.skipif(not CLI.exists(), reason="oracle/_ref/olm_b200 not built (needs the reference checkout at build time)")
+@pytest.mark.parametrize("pats,hay,cflags,mflags,expected", [
+    ("names.txt", "pseudo-kjv", [], [], "matcher_found.txt"),
+    ("names.txt", "pseudo-kjv", [], ["--longest", "--no-overlap"], "grep_found.txt"),
+    ("usernames.txt", "haystack_email.txt", [], ["--word-prefix"], "expected_word_prefix.txt"),
+    ("tlds.txt", "haystack_email.txt", [], ["--word-suffix"], "expected_word_suffix.txt"),
+    ("line_anchor_patterns.txt", "line_anchor_haystack.txt", [], ["--line-start", "--longest", "--no-overlap"],
+     "expected_line_start.txt"),
+    ("line_exact_match_patterns.txt", "line_exact_match_haystack.txt", [],
+     ["--line-start", "--line-end", "--longest", "--no-overlap"], "expected_line_exact_match.txt"),
+])
+def test_reference_cli_relinked(tmp_path, pats, hay, cflags, mflags, expected):
+    """`olm compile` + `olm match` of the UNMODIFIED omega_match/main.c (main.c:400-464 calls the
+    library, :89-133 prints `offset:bytes`) linked against libomega_match.so of this repository:
+    the command lines of the reference's ctest goldens (CMakeLists.txt smoke / aio_* tests)
+    produce the golden files byte for byte."""
+    import subprocess
+    (tmp_path / "p.txt").write_bytes(inputs.golden_data(pats))
+    (tmp_path / "h.txt").write_bytes(inputs.pseudo_kjv() if hay == "pseudo-kjv" else inputs.golden_data(hay))
+    olm, out = str(tmp_path / "p.olm"), str(tmp_path / "out.txt")
+    subprocess.run([str(CLI), "compile", *cflags, olm, str(tmp_path / "p.txt")], check=True, capture_output=True)
+    subprocess.run([str(CLI), "match", *mflags, "-o", out, olm, str(tmp_path / "h.txt")], check=True, capture_output=True)
+    got, want = open(out, "rb").read(), inputs.golden_data(expected)
+    assert got.replace(b"\r\n", b"\n") == want.replace(b"\r\n", b"\n"), (len(got), len(want), got[:200], want[:200])
+
+
 # ---- outputs of the reference library on seeded inputs (tests/golden/vectors.json) -----------
 
 @pytest.mark.parametrize("name", sorted(_CASES))

@@ -230,3 +230,22 @@ def test_key_bytes_choice(tmp_path, product_lib):
     assert kb(b"abcdefgh\nabcd\n") == 4
     assert kb(b"abcdefgh\nab\n") == 4
     assert kb(inputs.golden_data("names.txt")) == 4
+
+
+def test_reference_cli_compiles_through_the_product(tmp_path):
+    """The reference's unmodified CLI relinked against this library (oracle/Makefile, INTEGRATION.md
+    section 2): `olm compile` runs without a GPU and writes the file the library's compiler entry
+    point writes; the oracle loads it to the same pattern set."""
+    import subprocess
+    cli = inputs.GOLDEN.parent.parent / "oracle" / "_ref" / "olm_b200"
+    if not cli.exists():
+        pytest.skip("oracle/_ref/olm_b200 not built (needs the reference checkout at build time)")
+    pats = tmp_path / "p.txt"
+    pats.write_bytes(inputs.golden_data("names.txt"))
+    for flags, sf in (([], (False, False, False)), (["--ignore-case", "--ignore-punctuation", "--elide-whitespace"], (True, True, True))):
+        a, b = tmp_path / "cli.olm", tmp_path / "api.olm"
+        r = subprocess.run([str(cli), "compile", *flags, str(a), str(pats)], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        Compiler.compile_from_filename(str(b), str(pats), *sf)
+        assert a.read_bytes() == b.read_bytes()
+        assert Oracle.from_olm(str(a)).info()["digest"] == Oracle.from_patterns(pats.read_bytes(), *sf).info()["digest"]
