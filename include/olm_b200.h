@@ -194,6 +194,16 @@ int olm_cuda_match_shard(const omega_list_matcher_t *matcher, const void *dev_sl
                          int longest_only, int word_boundary, int word_prefix, int word_suffix,
                          int line_start, int line_end, olm_cuda_results_t *out);
 
+/* olm_cuda_match_shard() for a slice that lies in HOST memory (pinned memory copies fastest): the
+ * slice goes to the GPU in 256 MiB segments while the scan of the earlier segments runs -- the
+ * host-pointer efficiency of omega_list_matcher_match() (matcher.c:934-1019 takes host memory)
+ * for one rank of a multi-GPU job.  The records stay on the device. */
+int olm_cuda_match_shard_host(const omega_list_matcher_t *matcher, const void *host_slice,
+                              uint64_t slice_begin, uint64_t slice_len, uint64_t own_begin,
+                              uint64_t own_end, uint64_t global_size, const void *match_ptr_base,
+                              int longest_only, int word_boundary, int word_prefix, int word_suffix,
+                              int line_start, int line_end, olm_cuda_results_t *out);
+
 /* The greedy no-overlap filter (matcher.c:570-584) over `count` sorted device records, in
  * place; returns the kept count or -1. */
 int64_t olm_cuda_no_overlap(const omega_list_matcher_t *matcher, void *dev_records, uint64_t count);

@@ -97,6 +97,8 @@ ABI = [
     ("olm_cuda_match_device", _ci, [_vp, _vp, C.c_size_t, _vp] + _flags7 + [C.POINTER(CudaResultsC)]),
     ("olm_cuda_match_shard", _ci, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
      + [_ci] * 6 + [C.POINTER(CudaResultsC)]),
+    ("olm_cuda_match_shard_host", _ci, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
+     + [_ci] * 6 + [C.POINTER(CudaResultsC)]),
     ("olm_cuda_no_overlap", C.c_int64, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_sort_records", _ci, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_last_timing", _ci, [_vp, C.POINTER(CudaTimingC)]),

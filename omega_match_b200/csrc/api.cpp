@@ -238,6 +238,26 @@ int olm_cuda_match_shard(const omega_list_matcher_t *m, const void *dev_slice, u
   return rc;
 }
 
+int olm_cuda_match_shard_host(const omega_list_matcher_t *m, const void *host_slice, uint64_t slice_begin,
+                              uint64_t slice_len, uint64_t own_begin, uint64_t own_end, uint64_t global_size,
+                              const void *match_ptr_base, int longest_only, int word_boundary, int word_prefix,
+                              int word_suffix, int line_start, int line_end, olm_cuda_results_t *out) {
+  if (!m || !m->engine || !out || !host_slice) return -1;
+  olm::ScanRange r;
+  r.dev = nullptr;
+  r.slice_begin = slice_begin;
+  r.slice_len = slice_len;
+  r.own_begin = own_begin;
+  r.own_end = own_end;
+  r.global_size = global_size;
+  r.match_ptr_base = reinterpret_cast<uint64_t>(match_ptr_base);
+  const int rc = m->engine->match_shard_host(
+      static_cast<const uint8_t *>(host_slice), r,
+      to_flags(0, longest_only, word_boundary, word_prefix, word_suffix, line_start, line_end), out);
+  if (rc == 0 && m->stats) m->engine->collect_stats(m->stats);
+  return rc;
+}
+
 int64_t olm_cuda_no_overlap(const omega_list_matcher_t *m, void *dev_records, uint64_t count) {
   if (!m || !m->engine) return -1;
   return m->engine->no_overlap_inplace(dev_records, count);

@@ -111,6 +111,14 @@ struct EngineImpl {
   unsigned long long stat_counters[5] = {};
 };
 
+namespace {
+// index of the event after which the first `bytes` bytes of the slice are in HBM
+size_t seg_event_for(const EngineImpl &E, uint64_t bytes) {
+  if (E.seg_events.size() <= 1 || E.seg_bytes == 0 || bytes == 0) return 0;
+  return std::min<size_t>(E.seg_events.size() - 1, size_t((bytes - 1) / E.seg_bytes));
+}
+} // namespace
+
 Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string *err) {
   auto fail = [&](const std::string &m) -> Engine * {
     if (err) *err = m;
@@ -336,9 +344,9 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.num_tiles = (uint32_t)((P.scan_end - P.scan_begin + kTileBytes - 1) / kTileBytes);
         P.ticket = d_tickets + b;
         P.redo_flag = d_redo_flags + b;
-        if (E.streaming) { // the scan reads a halo past its segment: wait for the next one too
-          const size_t need = std::min<size_t>(E.seg_events.size() - 1, size_t(b) + 1);
-          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[need], 0));
+        if (E.streaming) { // the scan reads a halo past its positions: the copy has to be that far
+          const uint64_t upto = std::min<uint64_t>(r.slice_len, P.scan_end - r.slice_begin + kTileHalo + 16);
+          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[seg_event_for(E, upto)], 0));
         }
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
         if (E.want_stats) OLM_CUDA(stats_launch(P, E.stats, d_stats, E.sms, E.stream, &launches));
@@ -350,8 +358,10 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
       for (uint64_t b = 0; b < n_batches; ++b) {
         const uint64_t w0 = b * kBatchWindows;
         const uint32_t nw = (uint32_t)std::min<uint64_t>(kBatchWindows, n_windows - w0);
-        if (E.streaming)
-          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[std::min<size_t>(E.seg_events.size() - 1, size_t(b))], 0));
+        if (E.streaming) { // source bytes of this batch of windows
+          const uint64_t src_end = std::min<uint64_t>(n_own, (w0 + nw) * uint64_t(kWindowBytes));
+          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[seg_event_for(E, (r.own_begin - r.slice_begin) + src_end)], 0));
+        }
         TransformParams T{};
         T.src = static_cast<const uint8_t *>(r.dev);
         T.src_off = (r.own_begin - r.slice_begin) + w0 * kWindowBytes;
@@ -436,6 +446,61 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   return 0;
 }
 
+// H2D of `n` host bytes into the engine's haystack buffer: long inputs arrive in 256 MiB segments
+// on the copy stream while earlier segments are being scanned (match_device waits on the segment
+// events); short ones in one copy.  ev[4]/ev[5] bracket the copies.
+int Engine::stage_host(const uint8_t *src, size_t n) {
+  EngineImpl &E = *impl_;
+  const size_t padded = ((n + 15) & ~size_t(15)) + 256;
+  if (E.hay.ensure(padded)) return -1;
+  const uint64_t nseg = n >= kPipelineMin ? (n + kSegmentBytes - 1) / kSegmentBytes : 1;
+  while (E.seg_events.size() < nseg) {
+    cudaEvent_t ev;
+    OLM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    E.seg_events.push_back(ev);
+  }
+  while (E.seg_events.size() > nseg) { // seg_event_for() indexes by size: keep exactly nseg
+    cudaEventDestroy(E.seg_events.back());
+    E.seg_events.pop_back();
+  }
+  E.seg_bytes = nseg > 1 ? kSegmentBytes : 0;
+  OLM_CUDA(cudaEventRecord(E.ev[4], E.copy_stream));
+  for (uint64_t i = 0; i < nseg; ++i) {
+    const uint64_t b = i * kSegmentBytes, e = nseg > 1 ? std::min<uint64_t>(n, b + kSegmentBytes) : n;
+    OLM_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(E.hay.p) + b, src + b, e - b, cudaMemcpyHostToDevice, E.copy_stream));
+    OLM_CUDA(cudaEventRecord(E.seg_events[i], E.copy_stream));
+  }
+  OLM_CUDA(cudaEventRecord(E.ev[5], E.copy_stream));
+  return 0;
+}
+
+namespace {
+struct StreamingScope { // the device-resident entry points never see segments
+  EngineImpl &E;
+  explicit StreamingScope(EngineImpl &e) : E(e) { E.streaming = true; }
+  ~StreamingScope() { E.streaming = false; }
+};
+} // namespace
+
+// One rank's byte range from HOST memory: the slice is copied in segments while the scan of the
+// earlier segments runs; the records stay on the device (like match_device with a shard range).
+int Engine::match_shard_host(const uint8_t *host_slice, const ScanRange &range, const MatchFlags &f,
+                             olm_cuda_results_t *out) {
+  EngineImpl &E = *impl_;
+  OLM_CUDA(cudaSetDevice(E.device));
+  if (!host_slice || range.slice_len == 0) return -1;
+  if (stage_host(host_slice, range.slice_len)) return -1;
+  StreamingScope scope(E);
+  ScanRange r = range;
+  r.dev = E.hay.p;
+  if (match_device(r, f, out) != 0) return -1;
+  float ms = 0.f;
+  OLM_CUDA(cudaStreamSynchronize(E.copy_stream));
+  cudaEventElapsedTime(&ms, E.ev[4], E.ev[5]);
+  E.last.h2d_ms = ms;
+  return 0;
+}
+
 omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, const MatchFlags &f) {
   EngineImpl &E = *impl_;
   auto *results = static_cast<omega_match_results_t *>(std::malloc(sizeof(omega_match_results_t)));
@@ -448,38 +513,7 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
     std::free(results);
     return nullptr;
   };
-  if (cudaSetDevice(E.device) != cudaSuccess) return bail();
-  const size_t padded = ((n + 15) & ~size_t(15)) + 256;
-  if (E.hay.ensure(padded)) return bail();
-  // H2D: long haystacks arrive in 256 MiB segments on the copy stream while earlier segments
-  // are being scanned (match_device waits on the segment events); short ones in one copy.
-  const uint64_t nseg = n >= kPipelineMin ? (n + kSegmentBytes - 1) / kSegmentBytes : 1;
-  while (E.seg_events.size() < nseg) {
-    cudaEvent_t ev;
-    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail();
-    E.seg_events.push_back(ev);
-  }
-  while (E.seg_events.size() > nseg) { // match_device indexes by size: keep exactly nseg
-    cudaEventDestroy(E.seg_events.back());
-    E.seg_events.pop_back();
-  }
-  E.seg_bytes = nseg > 1 ? kSegmentBytes : 0;
-  cudaEventRecord(E.ev[4], E.copy_stream);
-  for (uint64_t i = 0; i < nseg; ++i) {
-    const uint64_t b = i * kSegmentBytes, e = nseg > 1 ? std::min<uint64_t>(n, b + kSegmentBytes) : n;
-    if (cudaMemcpyAsync(static_cast<uint8_t *>(E.hay.p) + b, haystack + b, e - b, cudaMemcpyHostToDevice,
-                        E.copy_stream) != cudaSuccess)
-      return bail();
-    cudaEventRecord(E.seg_events[i], E.copy_stream);
-  }
-  cudaEventRecord(E.ev[5], E.copy_stream);
-  struct StreamingScope { // the device-resident entry points never see segments
-    EngineImpl &E;
-    explicit StreamingScope(EngineImpl &e) : E(e) { E.streaming = true; }
-    ~StreamingScope() { E.streaming = false; }
-  } streaming_scope(E);
   ScanRange r;
-  r.dev = E.hay.p;
   r.slice_begin = 0;
   r.slice_len = n;
   r.own_begin = 0;
@@ -487,11 +521,8 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   r.global_size = n;
   r.match_ptr_base = reinterpret_cast<uint64_t>(haystack);
   olm_cuda_results_t dres;
-  if (match_device(r, f, &dres) != 0) return bail();
+  if (match_shard_host(haystack, r, f, &dres) != 0) return bail();
   float ms = 0.f;
-  cudaStreamSynchronize(E.copy_stream);
-  cudaEventElapsedTime(&ms, E.ev[4], E.ev[5]);
-  E.last.h2d_ms = ms;
   if (dres.count) {
     std::free(results->matches);
     const size_t rbytes = dres.count * sizeof(omega_match_result_t);

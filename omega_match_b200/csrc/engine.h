@@ -45,6 +45,9 @@ public:
   int match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_results_t *out);
   // Host input/output: H2D, match_device, D2H into a malloc'ed array.
   omega_match_results_t *match_host(const uint8_t *haystack, size_t n, const MatchFlags &f);
+  // A byte range (range.dev is ignored) whose slice lies in HOST memory: segmented H2D overlapped
+  // with the scan, device-resident records.
+  int match_shard_host(const uint8_t *host_slice, const ScanRange &range, const MatchFlags &f, olm_cuda_results_t *out);
 
   int64_t no_overlap_inplace(void *dev_records, uint64_t count);
   int sort_records(void *dev_records, uint64_t count);
@@ -57,6 +60,7 @@ public:
 
 private:
   Engine() = default;
+  int stage_host(const uint8_t *src, size_t n);
   EngineImpl *impl_ = nullptr;
 };
 

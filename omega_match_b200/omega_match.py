@@ -263,6 +263,19 @@ class Matcher:
             raise RuntimeError("olm_cuda_match_shard failed (see stderr)")
         return int(res.count), int(res.records or 0)
 
+    def match_shard_host(self, host_ptr: int, slice_begin: int, slice_len: int, own_begin: int, own_end: int,
+                         global_size: int, match_ptr_base: int = 0, **kw):
+        """match_shard() for a slice in host memory: segmented H2D overlapped with the scan; the
+        records stay on the device (include/olm_b200.h olm_cuda_match_shard_host)."""
+        if kw.get("no_overlap"):
+            raise ValueError("no_overlap crosses shards: apply Matcher.no_overlap_device on the gathered records")
+        f = _flag_ints(kw)[1:]
+        res = CudaResultsC()
+        if self._lib.olm_cuda_match_shard_host(self._matcher, host_ptr, slice_begin, slice_len, own_begin, own_end,
+                                               global_size, match_ptr_base, *f, C.byref(res)) != 0:
+            raise RuntimeError("olm_cuda_match_shard_host failed (see stderr)")
+        return int(res.count), int(res.records or 0)
+
     def no_overlap_device(self, records_ptr: int, count: int) -> int:
         n = self._lib.olm_cuda_no_overlap(self._matcher, records_ptr, count)
         if n < 0:

@@ -410,6 +410,43 @@ def test_shards_concatenate_to_the_whole(store_cache, world, kind):
             assert same_matches(got, want), f"{kind} x{world} {flags}: " + describe_diff(got, want)
 
 
+@pytest.mark.parametrize("kind", ["plain", "windowed"])
+def test_shard_from_host_memory_streams_like_the_device_path(store_cache, kind):
+    """olm_cuda_match_shard_host: a rank's slice in HOST memory, long enough (> 512 MiB) for the
+    segmented copy to overlap the scan, gives the records olm_cuda_match_shard gives for the same
+    slice on the device; both halves of a 2-way plan concatenate to the whole."""
+    torch = pytest.importorskip("torch")
+    import synth_torch
+    sf = (0, 0, 0) if kind == "plain" else (1, 0, 1)
+    pats = inputs.synth_long_patterns(3000) + ([b"the", b"ab"] if kind == "plain" else [])
+    path = store_cache("host-shard-" + kind, b"\n".join(pats), sf)
+    n = (1200 << 20) + 4096 * 3 + 77
+    hay = synth_torch.synth_haystack_torch(n, inputs.SEED_H5, device="cuda")
+    pb, pl = synth_torch.pack_patterns(pats, "cuda")
+    synth_torch.plant_torch(hay, pb, pl, 0x99)
+    torch.cuda.synchronize()
+    with Matcher(path) as m:
+        cnt, ptr = m.match_device(hay.data_ptr(), n)
+        whole = _as_matches(_device_records(torch, ptr, cnt))
+        parts = []
+        for s in shard_plan(n, 2, 24, windowed=any(sf)):
+            ln = s.slice_end - s.slice_begin
+            host = torch.empty(ln + 64, dtype=torch.uint8, pin_memory=True)
+            host[:ln].copy_(hay[s.slice_begin:s.slice_end])
+            torch.cuda.synchronize()
+            c1, p1 = m.match_shard_host(host.data_ptr(), s.slice_begin, ln, s.own_begin, s.own_end, n, 0)
+            a = _device_records(torch, p1, c1).clone()
+            assert m.last_timing()["h2d_ms"] > 0 and m.last_timing()["scan_launches"] >= (2 if kind == "plain" else 1)
+            dev = torch.zeros(((ln + 15) // 16) * 16 + 16, dtype=torch.uint8, device="cuda")
+            dev[:ln] = hay[s.slice_begin:s.slice_end]
+            torch.cuda.synchronize()
+            c2, p2 = m.match_shard(dev.data_ptr(), s.slice_begin, ln, s.own_begin, s.own_end, n, 0)
+            b = _device_records(torch, p2, c2)
+            assert c1 == c2 and bool((a[:, :2] == b[:, :2]).all())
+            parts.append(a)
+        assert Oracle.stream_digest(_as_matches(torch.cat(parts))) == Oracle.stream_digest(whole)
+
+
 def test_match_device_and_sort(store_cache):
     torch = pytest.importorskip("torch")
     pats = inputs.synth_long_patterns(2000) + [b"ab", b"the", b"abc", b"abcd"]
