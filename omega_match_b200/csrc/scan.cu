@@ -7,13 +7,15 @@
 // concatenate + radix sort of finalize_match_results (matcher.c:587-623, :258-325).
 //
 // Shape of scan_kernel
-//   * persistent CTAs (grid = #SMs) of 32 warps: 31 scanning warps and one producer warp.  Tiles of 8 KiB positions are handed out by an atomic ticket, so tile k
-//     is always started before k+1; inside a CTA the 32 chunks (512 positions) of a tile are
-//     grabbed dynamically by the scanning warps -- no warp waits for a slower one;
+//   * persistent CTAs (grid = #SMs) of 32 warps: 31 scanning warps and one producer warp.  Tiles
+//     of 4 KiB positions are handed out by an atomic ticket, so tile k is always started before
+//     k+1; inside a CTA the 8 chunks (512 positions) of a tile are grabbed dynamically by the
+//     scanning warps -- no warp waits for a slower one;
 //   * producer: each tile (+16 bytes in front, +112 behind) is brought into shared memory by
 //     ONE cp.async.bulk (TMA, 1-D, L2 evict-first) that completes on a `full` mbarrier; ring of
-//     2..4 stages; a stage is refilled as soon as its 32 chunks have arrived on `scanned` --
-//     no CTA-wide barrier anywhere;
+//     2..16 stages (as many as fit beside the filters; any depth -- stage and phase parity travel
+//     with the tile description); a stage is refilled as soon as its 8 chunks have arrived on
+//     `scanned` -- no CTA-wide barrier anywhere;
 //   * stage 1, every position, in registers:
 //       - stores whose patterns all start with a run of bytes from a small class (letters ...):
 //         SWAR range tests on the haystack words -> 1 bit per position (no memory access);
@@ -22,8 +24,8 @@
 //         store has 1..3 byte patterns);
 //     survivors are compacted, in position order, into the warp's queue Q1;
 //   * stage 2a, Q1 entries, 32 x kProbeUnroll at a time: position predicates, (class mode: the
-//     gram bitmap probe,) ONE 16-byte load of the gram's key bucket -- almost every false
-//     candidate ends here; key hits (and short-pattern candidates) are compacted into Q2;
+//     gram bitmap probe,) ONE 16-byte load (ld.global.cg) of the key's bucket -- almost every
+//     false candidate ends here; key hits (and short-pattern candidates) are compacted into Q2;
 //   * stage 2b, Q2 entries, 32 at a time, all lanes busy: the slot (pattern bytes 4..11 +
 //     length), remaining bytes against the pattern store, end predicates, the 4/3/2/1-byte
 //     sets; accepted matches are appended in candidate order (ballot + popc) to the chunk's
