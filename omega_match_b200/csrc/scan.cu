@@ -132,7 +132,9 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // Shared memory by 32-bit shared-space address.  The scanning warps never dereference a generic
 // pointer into shared memory: every generic access makes nvcc recompute the shared window base
 // (S2R SR_CgaCtaId + LEA, on the slow XU pipe) -- ~35 of them per chunk saturated that pipe.
-// one bucket of the key table.  (Variants measured at 1 M patterns)
+// One bucket of the key table.  The buckets never hit in L1 (a 32 MiB table probed at random), so
+// they are read with ld.global.cg -- cached in L2 only: 620 vs 608 GB/s at 1 M patterns with
+// __ldg; ld.global.nc.L1::no_allocate: 253.  OLM_KEY_LOAD=0 restores __ldg.
 #ifndef OLM_KEY_LOAD
 #define OLM_KEY_LOAD 1
 #endif
@@ -141,13 +143,7 @@ __device__ __forceinline__ uint4 ld_keys(const uint4 *p) {
   return __ldg(p);
 #else
   uint4 v;
-#if OLM_KEY_LOAD == 1
   asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#elif OLM_KEY_LOAD == 2
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#else
-  asm volatile("ld.global.nc.L1::evict_first.L2::evict_last.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-#endif
   return v;
 #endif
 }
