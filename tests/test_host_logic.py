@@ -249,3 +249,34 @@ def test_reference_cli_compiles_through_the_product(tmp_path):
         Compiler.compile_from_filename(str(b), str(pats), *sf)
         assert a.read_bytes() == b.read_bytes()
         assert Oracle.from_olm(str(a)).info()["digest"] == Oracle.from_patterns(pats.read_bytes(), *sf).info()["digest"]
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/olm_b200.h is a C header (no C++, CUDA or torch type): a C11 translation unit that
+    includes it, takes the address of every declared function and calls the entry points that
+    need no GPU compiles with gcc -pedantic and links against the built library."""
+    hdr_dir = inputs.GOLDEN.parent.parent / "include"
+    names = sorted(set(re.findall(r"\b((?:omega|olm)_[a-z0-9_]+)\s*\(", (hdr_dir / "olm_b200.h").read_text())))
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "olm_b200.h"\n#include <string.h>\n'
+        "static const void *table[] = {" + ", ".join(f"(const void *)(size_t){n}" for n in names) + "};\n"
+        "int main(void) {\n"
+        "  const char *v = omega_match_version();\n"
+        "  omega_list_matcher_compiler_t *c;\n"
+        "  if (!v || strlen(v) < 5) return 1;\n"
+        '  if (omega_list_matcher_is_compiled("/nonexistent/file.olm")) return 2;\n'
+        "  if (sizeof(omega_match_result_t) != 24) return 3;\n"
+        "  c = omega_list_matcher_compiler_create(\"%s\", 0, 0, 0);\n"
+        "  if (!c) return 4;\n"
+        '  if (omega_list_matcher_compiler_add_pattern(c, (const uint8_t *)"hello", 5) != 0) return 5;\n'
+        "  if (omega_list_matcher_compiler_destroy(c) != 0) return 6;\n"
+        "  return sizeof table / sizeof table[0] == %d ? 0 : 7;\n}\n" % (tmp_path / "abi.olm", len(names)))
+    exe = tmp_path / "abi"
+    lib = _lib.library_path()
+    r = subprocess.run(["gcc", "-std=c11", "-pedantic", "-Wall", "-Werror", f"-I{hdr_dir}", str(src), "-o", str(exe),
+                        f"-L{lib.parent}", "-lomega_match", f"-Wl,-rpath,{lib.parent}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
+    assert Oracle.from_olm(str(tmp_path / "abi.olm")).info()["long"] == 1
