@@ -7,7 +7,10 @@ bytes >= 0x80, very long lines -- and every store-flag combination:
     same size (`compiler.c:197-425`);
   * the oracle reads the same header facts from both files;
   * the REFERENCE matcher gives the same (offset, len) stream with either file, with and
-    without match flags.
+    without match flags;
+  * the device tables staged from the product's file (store.cpp: key buckets, slots, records,
+    bitmaps, class prefilter) pass their self check -- every pattern is found again through the
+    probe sequence the scan kernel uses (`olm_store_inspect`).
 Run by tests/test_host_logic.py in a subprocess (MALLOC_PERTURB_ as in ref_fuzz_worker.py).
 Exit code 0 = all trials agree.
 """
@@ -20,7 +23,11 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-from omega_match_b200 import Compiler  # noqa: E402
+import ctypes as C  # noqa: E402
+import os  # noqa: E402
+
+from omega_match_b200 import Compiler, _lib  # noqa: E402
+from omega_match_b200._lib import StoreInfoC  # noqa: E402
 from oracle.oracle import Oracle, RefLib  # noqa: E402
 
 FLAGS = ("no_overlap", "longest_only", "word_boundary", "word_prefix", "word_suffix", "line_start", "line_end")
@@ -86,6 +93,10 @@ def main(seed: int, trials: int) -> int:
         if Oracle.from_olm(mine).info() != Oracle.from_olm(theirs).info():
             print("INFO MISMATCH", buf, sf, Oracle.from_olm(mine).info(), Oracle.from_olm(theirs).info())
             return 1
+        for f in (mine, theirs):  # staging + self check of the device tables, from either writer's file
+            if _lib.load().olm_store_inspect(os.fsencode(f), C.byref(StoreInfoC())) != 0:
+                print("STAGING SELF CHECK FAILED", f.name, buf, sf)
+                return 1
         a, b = RefLib(mine), RefLib(theirs)
         for _ in range(3):
             hay = bytes(rng.choice(alph + b" \n") for _ in range(rng.choice([0, 3, 40, 1500, 6000])))
