@@ -97,6 +97,10 @@ struct EngineImpl {
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
+  // experimental stride-2 sampled mode (OLM_SAMPLE2=1 at create(); device_tables.h S2Store)
+  DevBuf d_s2keys, d_s2slots, d_s2recs;
+  S2Store s2;
+  ScanGeometry geo_s2;
   DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, misc, norm, map, windows, ghost, fscratch;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
@@ -167,6 +171,25 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && upload(impl->d_p23, staged.p23, &impl->ds.p23) == 0;
   ok = ok && upload(impl->d_set3, staged.set3, &impl->ds.set3) == 0;
   ok = ok && upload(impl->d_bitmap2, staged.bitmap2, &impl->ds.bitmap2) == 0;
+  if (const char *s2env = std::getenv("OLM_SAMPLE2"); s2env && s2env[0] == '1') {
+    // experimental, off by default: a second key table with two keys per pattern; launches without
+    // a position predicate then probe every second position only (scan.cu scan_chunk_s2)
+    StagedS2 t;
+    e = stage_store_s2(view, staged, &t);
+    if (e.empty() && check_staged_s2(view, staged, t) != 0) e = "internal error: stride-2 table failed its self check";
+    if (!e.empty()) {
+      delete eng;
+      return fail(e);
+    }
+    if (t.params.key_bytes) {
+      impl->s2 = t.params;
+      ok = ok && upload(impl->d_s2keys, t.keys, &impl->s2.keys) == 0;
+      ok = ok && upload(impl->d_s2slots, t.slots, &impl->s2.slots) == 0;
+      ok = ok && upload(impl->d_s2recs, t.recs, &impl->s2.recs) == 0;
+      impl->geo_s2 = scan_pick_geometry_s2(impl->smem_limit);
+      if (impl->geo_s2.stages == 0) impl->s2 = S2Store{};
+    }
+  }
   {
     StagedStats ss;
     e = stage_stats(view, &ss);
@@ -331,6 +354,9 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.flags = fl;
     P.stages = E.geo.stages;
     P.chunk_cap = E.geo.chunk_cap;
+    P.s2 = E.s2;
+    P.s2_stages = E.geo_s2.stages;
+    P.s2_chunk_cap = E.geo_s2.chunk_cap;
     P.tail_byte = 0;
 
     if (!windowed) {

@@ -43,7 +43,7 @@ ALPHABETS = (
 def random_list(rng):
     alph = rng.choice(ALPHABETS)
     n = rng.choice([1, 2, 5, 20, 100, 400])
-    lens = rng.choice([[1, 2, 3, 4], [1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 9, 12], [5, 6, 7, 8, 9, 13, 33], [4, 5], [40, 200, 700]])
+    lens = rng.choice([[1, 2, 3, 4], [1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 9, 12], [5, 6, 7, 8, 9, 13, 33], [4, 5], [6, 7, 9, 14, 24], [9, 10, 30], [40, 200, 700]])
     pats = []
     for _ in range(n):
         p = bytes(rng.choice(alph) for _ in range(rng.choice(lens)))

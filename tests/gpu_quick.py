@@ -33,14 +33,19 @@ def run(name, pats, sf, hay, flagsets):
                         print("   same set, order differs at", idx, got[idx], want[idx])
     return bad
 
-bad = 0
-names = inputs.case_patterns(dict(patterns="names", store_flags=(0,0,0)))
-fs = [(), ("word_boundary",), ("longest_only","no_overlap"), ("line_end","longest_only","no_overlap"), ("word_prefix",), ("word_suffix",), ("no_overlap",)]
-small = inputs.text_haystack(100000, 7)
-bad += run("names-small-text", names, (0,0,0), small, fs)
-bad += run("names-kjv", names, (0,0,0), np.frombuffer(inputs.pseudo_kjv(), dtype=np.uint8), [(), ("longest_only","no_overlap")])
-for c in inputs.vector_cases():
-    if c["name"] in ("names-text-c", "names-text-cpw", "synthshort-synth-plain", "synthlong-synth-plain", "names-sentence-plain", "synthshort-synth-cp"):
-        bad += run(c["name"], inputs.case_patterns(c), c["store_flags"], inputs.case_haystack(c), fs)
-print("TOTAL BAD", bad)
-sys.exit(1 if bad else 0)
+def main():
+    bad = 0
+    names = inputs.case_patterns(dict(patterns="names", store_flags=(0,0,0)))
+    fs = [(), ("word_boundary",), ("longest_only","no_overlap"), ("line_end","longest_only","no_overlap"), ("word_prefix",), ("word_suffix",), ("no_overlap",)]
+    small = inputs.text_haystack(100000, 7)
+    bad += run("names-small-text", names, (0,0,0), small, fs)
+    bad += run("names-kjv", names, (0,0,0), np.frombuffer(inputs.pseudo_kjv(), dtype=np.uint8), [(), ("longest_only","no_overlap")])
+    for c in inputs.vector_cases():
+        if c["name"] in ("names-text-c", "names-text-cpw", "synthshort-synth-plain", "synthlong-synth-plain", "names-sentence-plain", "synthshort-synth-cp"):
+            bad += run(c["name"], inputs.case_patterns(c), c["store_flags"], inputs.case_haystack(c), fs)
+    print("TOTAL BAD", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
