@@ -231,6 +231,8 @@ def workload_config(args, n_bytes=None, note=None):
          "patterns": args.patterns if args.workload == "cfg5" else None,
          "match_flags": [], "l2": "haystack is far larger than the 126 MB L2, no flush needed",
          "parallelism": f"byte-range shards x{args.gpus}"}
+    if os.environ.get("OLM_SAMPLE2", "")[:1] == "1":  # the experimental stride-2 scan is a different kernel: say so
+        c["scan_mode"] = "stride-2 sampled (OLM_SAMPLE2=1, experimental)"
     if note:
         c["note"] = note
     return c
