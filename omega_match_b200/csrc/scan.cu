@@ -58,6 +58,13 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 #define OLM_FAST_UNROLL 2
 #endif
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+// chunks a scanning warp takes per grab.  2 was slower with the 4-stage ring of an earlier version
+// (nothing left to prefetch into); kept as a build knob for the deeper rings.
+#ifndef OLM_GRAB
+#define OLM_GRAB 1
+#endif
+constexpr uint32_t kGrab = OLM_GRAB;
+static_assert(kGrab >= 1 && kTileChunks % kGrab == 0, "a grab stays inside one tile");
 #ifndef OLM_CLS_SKIP_BITMAP
 #define OLM_CLS_SKIP_BITMAP 0
 #endif
@@ -486,8 +493,34 @@ struct Scanner {
   static __device__ __forceinline__ uint32_t gather4(uint32_t m) { return __umulhi(m, 0x02040810u) & 0xFu; }
 
   // class bits of the 24 haystack bytes a lane holds (bit i = byte i is in the class), then
-  // bit i = bytes i .. i+run-1 are all in the class (run = 4 .. 8; i < 16)
-  __device__ __forceinline__ uint32_t class_runs16(const uint4 &v, const uint2 &nx, uint32_t run) const {
+  // bit i = bytes i .. i+run-1 are all in the class (run = 4, 5, 6 or 8; i < 16)
+  __device__ __forceinline__ uint32_t class_runs16(const uint4 &v, const uint2 &nx) const {
+    const ByteClass &c = P.st.cls;
+    const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
+    const uint32_t and4 = c.and4, lo0 = c.addlo[0], hi0 = c.addhi[0];
+    uint32_t a = 0;
+    if (c.n_ranges > 1) { // (uniform branch: one block of straight-line code per case)
+      const uint32_t lo1 = c.addlo[1], hi1 = c.addhi[1];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t t = w[i] & and4;
+        const uint32_t in = ((t + lo0) & ~(t + hi0)) | ((t + lo1) & ~(t + hi1));
+        a |= gather4(in & ~w[i] & 0x80808080u) << (4 * i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t t = w[i] & and4;
+        a |= gather4((t + lo0) & ~(t + hi0) & ~w[i] & 0x80808080u) << (4 * i);
+      }
+    }
+    a &= a >> 1;
+    a &= a >> 2;
+    a &= a >> (c.run - 4);
+    return a & 0xFFFFu;
+  }
+  // the same with the run length given (stride-2 mode: run = cls.run - 1, i.e. 4, 5 or 7)
+  __device__ __forceinline__ uint32_t class_runs16_run(const uint4 &v, const uint2 &nx, uint32_t run) const {
     const ByteClass &c = P.st.cls;
     const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
     const uint32_t and4 = c.and4, lo0 = c.addlo[0], hi0 = c.addhi[0];
@@ -520,7 +553,7 @@ struct Scanner {
     cg = 0;
     cp = 0;
     if (HAS_CLS) {
-      cg = class_runs16(v, lds64(src + 16), P.st.cls.run);
+      cg = class_runs16(v, lds64(src + 16));
       return;
     }
     const uint2 w45 = lds64(src + 16);
@@ -710,7 +743,7 @@ struct Scanner {
     const uint4 v = lds128(src);
     uint32_t cand = 0, cp = 0; // cp: candidates of the 1..3 byte patterns (HAS_P23)
     if (HAS_CLS) {
-      cand = class_runs16(v, lds64(src + 16), P.st.cls.run);
+      cand = class_runs16(v, lds64(src + 16));
     } else {
       const uint2 w45 = lds64(src + 16);
       const uint32_t w[6] = {v.x, v.y, v.z, v.w, w45.x, w45.y};
@@ -978,7 +1011,7 @@ struct Scanner {
     const uint32_t lpos = cbase + lane * 16; // a multiple of 16: odd k <=> odd position
     const uint32_t src = sb_off + kTilePre + lpos;
     const uint4 v = lds128(src);
-    uint32_t cand = class_runs16(v, lds64(src + 16), P.s2.run) & 0xAAAAu;
+    uint32_t cand = class_runs16_run(v, lds64(src + 16), P.s2.run) & 0xAAAAu;
     // positions p <= nscan: p == nscan (odd) still stands for the start nscan - 1
     if (lpos + 16 > T.nscan) cand &= lpos > T.nscan ? 0u : ((2u << (T.nscan - lpos)) - 1u);
     const uint32_t cnt = __popc(cand);
@@ -1291,9 +1324,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   uint32_t blk_left = 0;           // ... and how many are left
   for (;;) {
     uint32_t c = 0;
-    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c) : "r"(ctr32) : "memory");
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(c) : "r"(ctr32), "n"(kGrab) : "memory");
     c = __shfl_sync(kFull, c, 0);
-    const uint32_t k = c / kTileChunks, ci = c % kTileChunks;
+    const uint32_t k = c / kTileChunks, ci0 = c % kTileChunks;
     const uint32_t I32 = info32 + (k % kInfoRing) * (uint32_t)sizeof(StageInfo);
     // The mbarrier only tells two phases apart: make sure the stage is in OUR generation first.
     // (Chunks past the CTA's last tile may belong to an iteration that is never produced.)
@@ -1324,6 +1357,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
       T.tail = lds32(I32 + (uint32_t)offsetof(StageInfo, tail));
       T.first = (p0.x | p0.y) == 0;
     }
+    // (experiment knob OLM_GRAB: the kGrab chunks of a grab share the wait and the tile description)
+#if OLM_GRAB > 1
+#pragma unroll 1
+    for (uint32_t ci = ci0; ci < ci0 + kGrab; ++ci) {
+#else
+    {
+    const uint32_t ci = ci0;
+#endif
     const uint32_t cbase = ci * kChunkBytes;
     uint32_t n = 0, ovf = 0;
     if (cbase < T.nscan) {
@@ -1365,6 +1406,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     if (lane == 0)
       *reinterpret_cast<uint2 *>(P.chunk_desc + ((size_t)tile * kTileChunks + ci)) = make_uint2(d.count, d.temp_index);
     __syncwarp(); // the staging area is rewritten by the next chunk
+    }
   }
   sc.flush_stats(lane);
 }

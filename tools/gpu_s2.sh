@@ -14,3 +14,12 @@ done
 for s2 in 0 1; do
   OLM_SAMPLE2=$s2 timeout 300 python tools/profile_scan.py --size-gib 1 --workload cfg5 --iters 1 --flags longest_only,no_overlap 2>&1 | tail -1
 done
+# variant builds that travel with the snapshot (omega_match_b200/build/ does not): build them HERE first, e.g.
+#   make -C omega_match_b200/csrc -j8 BUILD=../build/v_grab2 OUT=../lib/v_grab2/libomega_match.so EXTRA=-DOLM_GRAB=2
+for lib in omega_match_b200/lib/v_*/libomega_match.so; do
+  [ -f "$lib" ] || continue
+  for s2 in 0 1; do
+    echo "== $lib OLM_SAMPLE2=$s2"
+    OMEGA_MATCH_LIB_PATH=$PWD/$lib OLM_SAMPLE2=$s2 timeout 300 python tools/profile_scan.py --size-gib 4 --workload cfg5 --iters 3 2>&1 | tail -1
+  done
+done
