@@ -113,6 +113,10 @@ struct EngineImpl {
   StatsTables stats;
   bool want_stats = false, stats_valid = false;
   unsigned long long stat_counters[5] = {};
+  // host haystacks scanned in spans (OLM_HOST_SPAN_BYTES, opt-in): bytes per span (0 = off) and the
+  // statistics of the spans before the last one (collect_stats adds them to the last call's)
+  uint64_t host_span = 0;
+  omega_match_stats_t span_acc{};
 };
 
 namespace {
@@ -189,6 +193,10 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
       impl->geo_s2 = scan_pick_geometry_s2(impl->smem_limit);
       if (impl->geo_s2.stages == 0) impl->s2 = S2Store{};
     }
+  }
+  if (const char *sp = std::getenv("OLM_HOST_SPAN_BYTES")) {
+    const unsigned long long v = std::strtoull(sp, nullptr, 10);
+    impl->host_span = (v + kWindowBytes - 1) / kWindowBytes * kWindowBytes; // whole 4 MiB windows
   }
   {
     StagedStats ss;
@@ -527,8 +535,71 @@ int Engine::match_shard_host(const uint8_t *host_slice, const ScanRange &range, 
   return 0;
 }
 
+// A host haystack in consecutive spans of `span` start positions (opt-in: OLM_HOST_SPAN_BYTES; written
+// for haystacks that should not be resident in HBM all at once; NOT yet run on a GPU -- DESIGN 7b).
+// Every span is a byte-range shard of the whole (same ownership rule, halo and
+// global-size predicates as the multi-GPU path), scanned from host memory with the copy
+// overlapped; the records of the spans are concatenated in order, and `no_overlap` -- the one
+// filter that crosses span edges -- runs once on the concatenation, on the device.
+omega_match_results_t *Engine::match_host_spans(const uint8_t *haystack, size_t n, const MatchFlags &f, uint64_t span) {
+  EngineImpl &E = *impl_;
+  static_assert(sizeof(Record) == sizeof(omega_match_result_t), "records are copied out verbatim");
+  const bool windowed = E.hdr.flags & kFlagAnyTransform;
+  MatchFlags fs = f;
+  fs.no_overlap = false;
+  std::vector<omega_match_result_t> all;
+  E.span_acc = omega_match_stats_t{};
+  for (uint64_t b = 0; b < n; b += span) {
+    const uint64_t e = std::min<uint64_t>(n, b + span);
+    ScanRange r;
+    r.own_begin = b;
+    r.own_end = e;
+    r.global_size = n;
+    r.match_ptr_base = reinterpret_cast<uint64_t>(haystack);
+    r.slice_begin = (windowed || b < 16) ? b : b - 16; // (b is a multiple of 4 MiB)
+    r.slice_len = (windowed ? e : std::min<uint64_t>(n, e + E.hdr.largest + 1)) - r.slice_begin;
+    olm_cuda_results_t d;
+    if (match_shard_host(haystack + r.slice_begin, r, fs, &d) != 0) return nullptr;
+    if (d.count) {
+      const size_t at = all.size();
+      all.resize(at + d.count);
+      if (cudaMemcpyAsync(all.data() + at, d.records, d.count * sizeof(Record), cudaMemcpyDeviceToHost, E.stream) != cudaSuccess ||
+          cudaStreamSynchronize(E.stream) != cudaSuccess)
+        return nullptr;
+    }
+    if (e < n) { // the last span's counters are collected by the caller, like those of a plain call
+      omega_match_stats_t acc = E.span_acc;
+      E.span_acc = omega_match_stats_t{};
+      collect_stats(&acc);
+      E.span_acc = acc;
+    }
+  }
+  uint64_t total = all.size();
+  if (f.no_overlap && total > 1) {
+    if (E.out.ensure(total * sizeof(Record))) return nullptr;
+    if (cudaMemcpyAsync(E.out.p, all.data(), total * sizeof(Record), cudaMemcpyHostToDevice, E.stream) != cudaSuccess) return nullptr;
+    const int64_t kept = no_overlap_inplace(E.out.p, total);
+    if (kept < 0) return nullptr;
+    total = uint64_t(kept);
+    if (cudaMemcpyAsync(all.data(), E.out.p, total * sizeof(Record), cudaMemcpyDeviceToHost, E.stream) != cudaSuccess ||
+        cudaStreamSynchronize(E.stream) != cudaSuccess)
+      return nullptr;
+  }
+  auto *results = static_cast<omega_match_results_t *>(std::malloc(sizeof(omega_match_results_t)));
+  if (!results) return nullptr;
+  results->matches = static_cast<omega_match_result_t *>(std::malloc(std::max<size_t>(1, total) * sizeof(omega_match_result_t)));
+  if (!results->matches) {
+    std::free(results);
+    return nullptr;
+  }
+  if (total) std::memcpy(results->matches, all.data(), total * sizeof(omega_match_result_t));
+  results->count = total;
+  return results;
+}
+
 omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, const MatchFlags &f) {
   EngineImpl &E = *impl_;
+  if (E.host_span && haystack && n > E.host_span) return match_host_spans(haystack, n, f, E.host_span);
   auto *results = static_cast<omega_match_results_t *>(std::malloc(sizeof(omega_match_results_t)));
   if (!results) return nullptr;
   results->count = 0;
@@ -609,7 +680,15 @@ void Engine::set_exact_stats(bool on) { impl_->want_stats = on; }
 
 void Engine::collect_stats(omega_match_stats_t *s) {
   if (!s) return;
-  const EngineImpl &E = *impl_;
+  EngineImpl &E = *impl_;
+  { // spans of a host haystack before the last one (match_host_spans); normally all zero
+    s->total_attempts += E.span_acc.total_attempts;
+    s->total_filtered += E.span_acc.total_filtered;
+    s->total_misses += E.span_acc.total_misses;
+    s->total_hits += E.span_acc.total_hits;
+    s->total_comparisons += E.span_acc.total_comparisons;
+    E.span_acc = omega_match_stats_t{};
+  }
   // counters written by the scan: [0] hits (key slots found + short matches accepted)
   // [1] misses (short candidates rejected by a predicate)  [2] comparisons  [3] key slots found
   if (E.stats_valid) {

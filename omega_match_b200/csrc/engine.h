@@ -61,6 +61,7 @@ public:
 private:
   Engine() = default;
   int stage_host(const uint8_t *src, size_t n);
+  omega_match_results_t *match_host_spans(const uint8_t *haystack, size_t n, const MatchFlags &f, uint64_t span);
   EngineImpl *impl_ = nullptr;
 };
 
