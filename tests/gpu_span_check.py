@@ -30,7 +30,7 @@ def main() -> int:
     for n in ((4 << 20) + 1, (8 << 20), (9 << 20) + 12345, (21 << 20) + 7):
         hay = inputs.text_haystack(n, 7 + n)
         # matches across every span edge: a long name written over each 4 MiB boundary
-        for edge in range(4 << 20, n, 4 << 20):
+        for edge in range(4 << 20, n - 6, 4 << 20):
             hay[edge - 5:edge + 6] = np.frombuffer(b"Christopher", dtype=np.uint8)
         bad += run(f"names-spans-n{n}", names, (0, 0, 0), hay, FS)
         bad += run(f"names-cpw-spans-n{n}", names, (1, 1, 1), hay, FS[:3])
