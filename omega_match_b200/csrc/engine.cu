@@ -192,6 +192,10 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
       ok = ok && upload(impl->d_s2recs, t.recs, &impl->s2.recs) == 0;
       impl->geo_s2 = scan_pick_geometry_s2(impl->smem_limit);
       if (impl->geo_s2.stages == 0) impl->s2 = S2Store{};
+      if (std::getenv("OLM_S2_DEBUG"))
+        std::fprintf(stderr, "libomega_match(b200): stride-2 mode %s: K=%u run=%u keys=%u stages=%u cap=%u\n",
+                     impl->s2.key_bytes ? "on" : "off", t.params.key_bytes, t.params.run, t.n_keys, impl->geo_s2.stages,
+                     impl->geo_s2.chunk_cap);
     }
   }
   if (const char *sp = std::getenv("OLM_HOST_SPAN_BYTES")) {

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """GPU-box checker for the EXPERIMENTAL stride-2 sampled mode (OLM_SAMPLE2=1; DESIGN.md 7b,
 device_tables.h S2Store, scan.cu scan_chunk_s2).  Not collected by pytest: the mode is off by
-default and has not run on a GPU yet (it was written after this round's GPU budget was spent).
+default; `--quick` ran bit-exact on a B200 (profiles/r1_s2_quick_parity.log), the full set and the
+throughput run are for the next GPU session.
 
   OLM_SAMPLE2=1 python tests/gpu_s2_check.py            # product (sampled mode) vs oracle
   OLM_SAMPLE2=1 python tools/profile_scan.py --size-gib 4 --workload cfg5 --iters 3   # throughput
@@ -30,6 +31,17 @@ FS = [(), ("longest_only",), ("no_overlap",), ("longest_only", "no_overlap"), ("
 def main() -> int:
     bad = 0
     pats = inputs.synth_long_patterns(3000)
+    if "--quick" in sys.argv:  # a few seconds: edges, coinciding keys, overflow -> redo, one windowed store
+        for n in (7, 513, 4097, 100_003, (1 << 20) + 1):
+            hay = inputs.plant(inputs.synth_haystack(n, inputs.SEED_H5 + n), pats, 0x51 + n, block=256)
+            bad += run(f"synth3000-n{n}", b"\n".join(pats), (0, 0, 0), hay, FS[:4])
+        adv = [b"aaaaaaa", b"aaaaaaaa", b"aaaaaab", b"baaaaaa", b"abababab", b"bababababa", b"abcdefgh", b"bcdefghi", b"xabcdefgh"]
+        text = (b"xabcdefghijklmnopqrstuvwxyza aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaaab " * 200)[:9001]
+        bad += run("adversarial-alpha", b"\n".join(adv), (0, 0, 0), np.frombuffer(text, dtype=np.uint8).copy(), FS[:4])
+        bad += run("dense-a", b"\n".join(adv), (0, 0, 0), np.full(50_000, ord("a"), dtype=np.uint8), FS[:2])
+        bad += run("synth3000-ci", b"\n".join(pats), (1, 0, 0), inputs.plant(inputs.synth_haystack(5_000_001, 99), pats, 5, block=512), FS[:2])
+        print("TOTAL BAD", bad)
+        return 1 if bad else 0
     # planted patterns at odd and even offsets, chunk / tile / end-of-buffer edges
     for n in (5, 6, 7, 511, 512, 513, 4095, 4096, 4097, 8193, 100_003, 1 << 20, (1 << 22) + 77):
         hay = inputs.plant(inputs.synth_haystack(n, inputs.SEED_H5 + n), pats, 0x51 + n, block=256)
