@@ -1,10 +1,10 @@
 """CPU model of the experimental stride-2 sampled scan (scan.cu `scan_chunk_s2` / `verify_s2`,
 device_tables.h `S2Store`) against the oracle.
 
-The CUDA path of that mode has not run on a GPU yet; this test pins the
-ALGORITHM the kernel implements -- which positions are probed, which entries a key lists and in
-which order, the ownership and end-of-buffer rules -- so that what is left to validate on the GPU
-is the transcription, not the idea:
+The CUDA path of that mode is off by default and has only a quick parity run on a GPU behind it
+(DESIGN.md 7b item 4); this test pins the ALGORITHM the kernel implements -- which positions are
+probed, which entries a key lists and in which order, the ownership and end-of-buffer rules -- so
+that what the GPU checks validate is the transcription, not the idea:
 
   * tiles of 4096 start positions, chunks of 512; only the ODD tile-relative positions p <= nscan
     are probed, and only when K bytes are left from p on;
