@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 
@@ -94,7 +95,12 @@ omega_list_matcher_t *omega_list_matcher_create(const char *path, int case_insen
   m->temp_path = temp_path;
   m->file = olm::map_whole_file(load.c_str(), &m->file_size, false);
   std::string err = "cannot map file";
-  if (m->file) m->engine = olm::Engine::create(m->file, m->file_size, default_device(), &err);
+  try { // no exception crosses the C ABI: a store that asks for absurd allocations is a bad file
+    if (m->file) m->engine = olm::Engine::create(m->file, m->file_size, default_device(), &err);
+  } catch (const std::exception &ex) {
+    m->engine = nullptr;
+    err = std::string("malformed store (") + ex.what() + ")";
+  }
   if (!m->engine) {
     std::fprintf(stderr, "libomega_match(b200): cannot create matcher from %s: %s\n", path, err.c_str());
     omega_list_matcher_destroy(m);
@@ -289,14 +295,15 @@ int olm_store_inspect(const char *compiled_file, olm_store_info_t *out) {
   olm::StoreView v;
   const std::string err = olm::parse_store(f, n, &v);
   int rc = -1;
-  if (err.empty()) {
+  if (err.empty()) try {
     olm::StagedStore s;
     olm::FilterBudget b;
     const std::string e2 = olm::stage_store(v, b, &s);
     // (the second key table of the experimental stride-2 mode is staged and checked as well)
     olm::StagedS2 s2;
+    olm::StagedStats ss; // (and the tables of the exact statistics: everything create() stages)
     if (e2.empty() && olm::check_staged_store(v, s) == 0 && olm::stage_store_s2(v, s, &s2).empty() &&
-        olm::check_staged_s2(v, s, s2) == 0) {
+        olm::check_staged_s2(v, s, s2) == 0 && olm::stage_stats(v, &ss).empty()) {
       if (std::getenv("OLM_S2_DEBUG"))
         std::fprintf(stderr, "libomega_match(b200): stride-2 table: K=%u run=%u keys=%u buckets=%zu recs=%zu\n",
                      s2.params.key_bytes, s2.params.run, s2.n_keys, s2.keys.size(), s2.recs.size());
@@ -327,6 +334,9 @@ int olm_store_inspect(const char *compiled_file, olm_store_info_t *out) {
     } else {
       std::fprintf(stderr, "libomega_match(b200): %s: %s\n", compiled_file, e2.empty() ? "self check failed" : e2.c_str());
     }
+  } catch (const std::exception &ex) {
+    std::fprintf(stderr, "libomega_match(b200): %s: malformed store (%s)\n", compiled_file, ex.what());
+    rc = -1;
   } else {
     std::fprintf(stderr, "libomega_match(b200): %s: %s\n", compiled_file, err.c_str());
   }

@@ -108,7 +108,7 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
 
   // ---- walk the bucket blob: [u32 gram][u32 count][{u64 off,u32 len,u32 0} x count]
   std::vector<BucketRef> buckets;
-  buckets.reserve(h.occupied);
+  buckets.reserve(size_t(std::min<uint64_t>(h.occupied, h.blob_bytes / (8 + kBucketRecordBytes)))); // (the header is not trusted)
   uint64_t n_recs_multi = 0, n_long = 0;
   for (uint64_t p = 0; p < h.blob_bytes;) {
     if (p + 8 > h.blob_bytes) return "truncated bucket header";
@@ -406,7 +406,16 @@ std::string stage_stats(const StoreView &v, StagedStats *s) {
   s->bloom.assign(std::max<size_t>(1, v.bloom_bits / 64), 0);
   std::memcpy(s->bloom.data(), v.bloom, std::min<size_t>(s->bloom.size() * 8, h.bloom_bytes));
   s->bloom_mask = v.bloom_bits - 1;
-  const uint32_t lg = std::max<uint32_t>(4, ceil_log2(std::max<uint64_t>(1, h.occupied) * 2));
+  // (sized by the buckets the bucket data really holds, not by the header's count: a wrong count
+  // must neither exhaust memory nor leave the open-addressing insert below without a free place)
+  uint64_t n_buckets = 0;
+  for (uint64_t p = 0; p < h.blob_bytes; ++n_buckets) {
+    if (p + 8 > h.blob_bytes) return "truncated bucket header";
+    const uint32_t count = rd32(v.blob + p + 4);
+    if (count == 0 || p + 8 + uint64_t(count) * kBucketRecordBytes > h.blob_bytes) return "bucket runs past the bucket data";
+    p += 8 + uint64_t(count) * kBucketRecordBytes;
+  }
+  const uint32_t lg = std::max<uint32_t>(4, ceil_log2(std::max<uint64_t>(1, n_buckets) * 2));
   if (lg > 30) return "too many buckets";
   s->map.assign(size_t(1) << lg, make_uint2(0, 0));
   s->map_shift = 32 - lg;
