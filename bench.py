@@ -20,6 +20,11 @@ A step = one pass of the hot path over the whole haystack:
             bounded prefix of the same haystack (the reference needs ~table_size probes per
             Bloom false positive, SURVEY F8, so the full size is out of reach).
 
+  experimental -- (N=1, cfg5; `--no-experimental` skips it) the stride-2 sampled scan, which is OFF
+            by default (OLM_SAMPLE2=1), on the same workload in a process of
+            its own: device-timed GB/s and whether it reports the same number of matches as the
+            default path.  Reported beside the line's numbers, never as `value`.
+
 `--impl reference` times only that CPU reference on the same workload definition.
 """
 from __future__ import annotations
@@ -433,9 +438,40 @@ def run_ours(args):
             os.unlink(tmpname)
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    # ---- experimental leg (N=1, cfg5): the stride-2 sampled scan (OLM_SAMPLE2=1, off by default,
+    # DESIGN.md 7b item 4) on the same workload, in a process of its own so that nothing it does can
+    # touch the numbers above.  Reported beside them, never as `value`.
+    if world == 1 and args.workload == "cfg5" and not args.no_experimental:
+        del hay
+        torch.cuda.empty_cache()
+        line["experimental"] = stride2_leg(args, total_matches)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stride2_leg(args, expected_matches):
+    """tools/profile_scan.py with OLM_SAMPLE2=1: same generator, seeds and size as the main leg, so the
+    match count must equal the main leg's; device-timed like `roofline.achieved`."""
+    out = {"scan_mode": "stride-2 sampled (OLM_SAMPLE2=1)", "unit": UNIT}
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), "--size-gib", str(args.size_gib),
+                            "--patterns", str(args.patterns), "--workload", "cfg5", "--iters", "4"],
+                           env=dict(os.environ, OLM_SAMPLE2="1", OLM_S2_DEBUG="1"), capture_output=True, text=True,
+                           timeout=300)
+        iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
+        if r.returncode != 0 or not iters:
+            out["error"] = (r.stderr or r.stdout)[-300:]
+            return out
+        best = 0.0
+        for ln in iters[1:] or iters:  # the first call sizes the result buffers
+            best = max(best, float(ln.split("->")[1].split("GB/s")[0]))
+        cnt = int(iters[-1].split(":")[1].split("matches")[0])
+        out.update({"achieved": best, "matches_per_step": cnt, "same_match_count_as_default_path": cnt == expected_matches,
+                    "engaged": "stride-2 mode on" in r.stderr})
+    except Exception as e:  # reported, never required
+        out["error"] = repr(e)[:300]
+    return out
 
 
 def main():
@@ -448,6 +484,7 @@ def main():
     ap.add_argument("--size-gib", type=float, default=16.0)
     ap.add_argument("--patterns", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-experimental", action="store_true", help="skip the stride-2 leg (N=1, cfg5)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")
