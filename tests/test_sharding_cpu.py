@@ -96,6 +96,8 @@ def _gloo_worker(rank: int, world: int, port: int, out_path: str):
     try:
         pats = inputs.synth_long_patterns(2000) + [b"ab", b"the", b"King"]
         hay = inputs.plant(inputs.synth_haystack(200_000, 99), pats, 6, block=1024)
+        if world > 2:  # one rank without a single match: its gather leg is skipped on both sides
+            hay[shard_plan(hay.size, world, 24, False)[1].slice_begin:shard_plan(hay.size, world, 24, False)[1].slice_end] = 0x23
         o = Oracle.from_patterns(pats)
         s = shard_plan(hay.size, world, 24, False)[rank]
         mine = scan_shard_with_oracle(o, hay, s, False)
@@ -122,4 +124,14 @@ def test_gather_over_gloo_world2(tmp_path):
     import torch.multiprocessing as mp
     out = tmp_path / "result.txt"
     mp.spawn(_gloo_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    assert out.read_text() == "OK"
+
+
+def test_gather_over_gloo_world4_with_an_empty_rank(tmp_path):
+    """Four ranks, one of them with no match at all (its send and the matching receive are both
+    skipped); the result on rank 0 is still the unsharded stream."""
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    out = tmp_path / "result4.txt"
+    mp.spawn(_gloo_worker, args=(4, _free_port(), str(out)), nprocs=4, join=True)
     assert out.read_text() == "OK"
