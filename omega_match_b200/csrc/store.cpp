@@ -133,9 +133,14 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
   if (h.store_bytes) std::memcpy(s->store.data(), v.patterns, size_t(h.store_bytes));
 
   // ---- keys + slots.  A key covers the first K bytes of a pattern (device_tables.h).
-  uint32_t min_long = 0xFFFFFFFFu;
+  uint32_t min_long = 0xFFFFFFFFu, max_long = 0;
   for (const BucketRef &b : buckets)
-    for (uint32_t j = 0; j < b.count; ++j) min_long = std::min(min_long, rd32(b.recs + 16ull * j + 8));
+    for (uint32_t j = 0; j < b.count; ++j) {
+      min_long = std::min(min_long, rd32(b.recs + 16ull * j + 8));
+      max_long = std::max(max_long, rd32(b.recs + 16ull * j + 8));
+    }
+  // (shard halos are sized from the header's longest pattern: it must not understate the records)
+  if (max_long > h.largest) return "header understates the longest pattern";
   DeviceStore &d = s->params;
   // (stores with 1..4 byte patterns keep 4-byte keys: the 4-byte patterns are keys themselves, and
   // the kernels for short-pattern stores hash four bytes only)
