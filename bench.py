@@ -452,25 +452,34 @@ def run_ours(args):
 
 def stride2_leg(args, expected_matches):
     """tools/profile_scan.py with OLM_SAMPLE2=1: same generator, seeds and size as the main leg, so the
-    match count must equal the main leg's; device-timed like `roofline.achieved`."""
+    match count must equal the main leg's; device-timed like `roofline.achieved`.  Run twice: with the
+    key table at load <= 0.125 (64 MiB at 1 M patterns, the mode's default) and at load <= 0.25 (32 MiB:
+    more full buckets, but half the L2 footprint)."""
     out = {"scan_mode": "stride-2 sampled (OLM_SAMPLE2=1)", "unit": UNIT}
-    try:
-        r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), "--size-gib", str(args.size_gib),
-                            "--patterns", str(args.patterns), "--workload", "cfg5", "--iters", "4"],
-                           env=dict(os.environ, OLM_SAMPLE2="1", OLM_S2_DEBUG="1"), capture_output=True, text=True,
-                           timeout=300)
-        iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
-        if r.returncode != 0 or not iters:
-            out["error"] = (r.stderr or r.stdout)[-300:]
-            return out
-        best = 0.0
-        for ln in iters[1:] or iters:  # the first call sizes the result buffers
-            best = max(best, float(ln.split("->")[1].split("GB/s")[0]))
-        cnt = int(iters[-1].split(":")[1].split("matches")[0])
-        out.update({"achieved": best, "matches_per_step": cnt, "same_match_count_as_default_path": cnt == expected_matches,
-                    "engaged": "stride-2 mode on" in r.stderr})
-    except Exception as e:  # reported, never required
-        out["error"] = repr(e)[:300]
+    for key, extra in (("achieved", "1"), ("achieved_half_size_key_table", "0")):
+        try:
+            r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), "--size-gib", str(args.size_gib),
+                                "--patterns", str(args.patterns), "--workload", "cfg5", "--iters", "4"],
+                               env=dict(os.environ, OLM_SAMPLE2="1", OLM_S2_DEBUG="1", OLM_S2_KEY_EXTRA_LOG2=extra),
+                               capture_output=True, text=True, timeout=300)
+            iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
+            if r.returncode != 0 or not iters:
+                out[key] = None
+                out["error"] = (r.stderr or r.stdout)[-300:]
+                continue
+            best = 0.0
+            for ln in iters[1:] or iters:  # the first call sizes the result buffers
+                best = max(best, float(ln.split("->")[1].split("GB/s")[0]))
+            cnt = int(iters[-1].split(":")[1].split("matches")[0])
+            out[key] = best
+            if extra == "1":
+                out.update({"matches_per_step": cnt, "same_match_count_as_default_path": cnt == expected_matches,
+                            "engaged": "stride-2 mode on" in r.stderr})
+            else:
+                out["same_match_count_half_size"] = cnt == expected_matches
+        except Exception as e:  # reported, never required
+            out[key] = None
+            out["error"] = repr(e)[:300]
     return out
 
 
