@@ -165,6 +165,14 @@ typedef struct {
   uint64_t matches_before_filter;
 } olm_cuda_timing_t;
 
+/* Environment variables read at omega_list_matcher_create():
+ *   OLM_CUDA_DEVICE=<i>       default GPU (see olm_cuda_set_default_device)
+ *   OLM_EXACT_STATS=1         see olm_cuda_set_exact_stats
+ *   OLM_SAMPLE2=1             EXPERIMENTAL, off by default: stride-2 sampled scan for stores whose
+ *                             patterns all have >= 6 bytes (same results)
+ *   OLM_HOST_SPAN_BYTES=<n>   EXPERIMENTAL, off by default: omega_list_matcher_match scans host
+ *                             haystacks longer than n bytes in spans of n bytes (bounded device
+ *                             memory; same results) */
 int olm_cuda_device_count(void);
 /* Choose the GPU a matcher lives on BEFORE create (process wide default: device 0 or
  * $OLM_CUDA_DEVICE). */
