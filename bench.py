@@ -20,6 +20,9 @@ A step = one pass of the hot path over the whole haystack:
             bounded prefix of the same haystack (the reference needs ~table_size probes per
             Bloom false positive, SURVEY F8, so the full size is out of reach).
 
+  other_workloads -- (N=1, cfg5 runs only; skipped by `--no-experimental`) the default path on names.txt
+            and on names.txt compiled with all three transform flags (4 MiB normalisation windows),
+            4 GiB synthetic text each, device-timed, in processes of their own.
   experimental -- (N=1, cfg5; `--no-experimental` skips it) the stride-2 sampled scan, which is OFF
             by default (OLM_SAMPLE2=1), on the same workload in a process of
             its own: device-timed GB/s and whether it reports the same number of matches as the
@@ -445,9 +448,29 @@ def run_ours(args):
         del hay
         torch.cuda.empty_cache()
         line["experimental"] = stride2_leg(args, total_matches)
+        # the default path on the store shapes of BASELINE configs[0..2] (names.txt: 29 k patterns with
+        # 1..4 byte ones; the same compiled with ignore-case + ignore-punctuation + elide-whitespace, i.e.
+        # through the 4 MiB normalisation windows), 4 GiB synthetic text each, device-timed
+        line["other_workloads"] = {w: profile_scan_leg(["--size-gib", "4", "--workload", w, "--iters", "3"], {})
+                                   for w in ("names", "names-cpw")}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def profile_scan_leg(argv, env):
+    """One run of tools/profile_scan.py in a process of its own -> {"achieved": best GB/s after the
+    first call, "matches_per_step": n} or {"error": ...}.  Reported, never required."""
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), *argv], env=dict(os.environ, **env),
+                           capture_output=True, text=True, timeout=300)
+        iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
+        if r.returncode != 0 or not iters:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        best = max(float(ln.split("->")[1].split("GB/s")[0]) for ln in (iters[1:] or iters))
+        return {"achieved": best, "unit": UNIT, "matches_per_step": int(iters[-1].split(":")[1].split("matches")[0])}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
 
 
 def stride2_leg(args, expected_matches):
