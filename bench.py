@@ -458,12 +458,24 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_EXTRA_DEADLINE = [None]  # all extra legs together get 200 s; a leg that would not fit is skipped
+
+
+def _leg_timeout():
+    if _EXTRA_DEADLINE[0] is None:
+        _EXTRA_DEADLINE[0] = time.time() + 200.0
+    return min(75.0, _EXTRA_DEADLINE[0] - time.time())
+
+
 def profile_scan_leg(argv, env):
     """One run of tools/profile_scan.py in a process of its own -> {"achieved": best GB/s after the
     first call, "matches_per_step": n} or {"error": ...}.  Reported, never required."""
     try:
+        tmo = _leg_timeout()
+        if tmo < 15.0:
+            return {"error": "skipped: the extra legs' time budget is used up"}
         r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), *argv], env=dict(os.environ, **env),
-                           capture_output=True, text=True, timeout=300)
+                           capture_output=True, text=True, timeout=tmo)
         iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
         if r.returncode != 0 or not iters:
             return {"error": (r.stderr or r.stdout)[-300:]}
@@ -481,10 +493,15 @@ def stride2_leg(args, expected_matches):
     out = {"scan_mode": "stride-2 sampled (OLM_SAMPLE2=1)", "unit": UNIT}
     for key, extra in (("achieved", "1"), ("achieved_half_size_key_table", "0")):
         try:
+            tmo = _leg_timeout()
+            if tmo < 15.0:
+                out[key] = None
+                out["error"] = "skipped: the extra legs' time budget is used up"
+                continue
             r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), "--size-gib", str(args.size_gib),
                                 "--patterns", str(args.patterns), "--workload", "cfg5", "--iters", "4"],
                                env=dict(os.environ, OLM_SAMPLE2="1", OLM_S2_DEBUG="1", OLM_S2_KEY_EXTRA_LOG2=extra),
-                               capture_output=True, text=True, timeout=300)
+                               capture_output=True, text=True, timeout=tmo)
             iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
             if r.returncode != 0 or not iters:
                 out[key] = None
