@@ -23,10 +23,6 @@ A step = one pass of the hot path over the whole haystack:
   other_workloads -- (N=1, cfg5 runs only; skipped by `--no-experimental`) the default path on names.txt
             and on names.txt compiled with all three transform flags (4 MiB normalisation windows),
             4 GiB synthetic text each, device-timed, in processes of their own.
-  experimental -- (N=1, cfg5; `--no-experimental` skips it) the stride-2 sampled scan, which is OFF
-            by default (OLM_SAMPLE2=1), on the same workload in a process of
-            its own: device-timed GB/s and whether it reports the same number of matches as the
-            default path.  Reported beside the line's numbers, never as `value`.
 
 `--impl reference` times only that CPU reference on the same workload definition.
 """
@@ -239,8 +235,6 @@ def workload_config(args, n_bytes=None, note=None):
          "patterns": args.patterns if args.workload == "cfg5" else None,
          "match_flags": [], "l2": "haystack is far larger than the 126 MB L2, no flush needed",
          "parallelism": f"byte-range shards x{args.gpus}"}
-    if os.environ.get("OLM_SAMPLE2", "")[:1] == "1":  # the experimental stride-2 scan is a different kernel: say so
-        c["scan_mode"] = "stride-2 sampled (OLM_SAMPLE2=1, experimental)"
     if note:
         c["note"] = note
     return c
@@ -441,13 +435,9 @@ def run_ours(args):
             os.unlink(tmpname)
         except Exception as e:  # the baseline is reported, never required
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
-    # ---- experimental leg (N=1, cfg5): the stride-2 sampled scan (OLM_SAMPLE2=1, off by default,
-    # DESIGN.md 7b item 4) on the same workload, in a process of its own so that nothing it does can
-    # touch the numbers above.  Reported beside them, never as `value`.
     if world == 1 and args.workload == "cfg5" and not args.no_experimental:
         del hay
         torch.cuda.empty_cache()
-        line["experimental"] = stride2_leg(args, total_matches)
         # the default path on the store shapes of BASELINE configs[0..2] (names.txt: 29 k patterns with
         # 1..4 byte ones; the same compiled with ignore-case + ignore-punctuation + elide-whitespace, i.e.
         # through the 4 MiB normalisation windows), 4 GiB synthetic text each, device-timed
@@ -485,44 +475,6 @@ def profile_scan_leg(argv, env):
         return {"error": repr(e)[:300]}
 
 
-def stride2_leg(args, expected_matches):
-    """tools/profile_scan.py with OLM_SAMPLE2=1: same generator, seeds and size as the main leg, so the
-    match count must equal the main leg's; device-timed like `roofline.achieved`.  Run twice: with the
-    key table at load <= 0.125 (64 MiB at 1 M patterns, the mode's default) and at load <= 0.25 (32 MiB:
-    more full buckets, but half the L2 footprint)."""
-    out = {"scan_mode": "stride-2 sampled (OLM_SAMPLE2=1)", "unit": UNIT}
-    for key, extra in (("achieved", "1"), ("achieved_half_size_key_table", "0")):
-        try:
-            tmo = _leg_timeout()
-            if tmo < 15.0:
-                out[key] = None
-                out["error"] = "skipped: the extra legs' time budget is used up"
-                continue
-            r = subprocess.run([sys.executable, str(ROOT / "tools" / "profile_scan.py"), "--size-gib", str(args.size_gib),
-                                "--patterns", str(args.patterns), "--workload", "cfg5", "--iters", "4"],
-                               env=dict(os.environ, OLM_SAMPLE2="1", OLM_S2_DEBUG="1", OLM_S2_KEY_EXTRA_LOG2=extra),
-                               capture_output=True, text=True, timeout=tmo)
-            iters = [ln for ln in r.stdout.splitlines() if ln.startswith("iter ")]
-            if r.returncode != 0 or not iters:
-                out[key] = None
-                out["error"] = (r.stderr or r.stdout)[-300:]
-                continue
-            best = 0.0
-            for ln in iters[1:] or iters:  # the first call sizes the result buffers
-                best = max(best, float(ln.split("->")[1].split("GB/s")[0]))
-            cnt = int(iters[-1].split(":")[1].split("matches")[0])
-            out[key] = best
-            if extra == "1":
-                out.update({"matches_per_step": cnt, "same_match_count_as_default_path": cnt == expected_matches,
-                            "engaged": "stride-2 mode on" in r.stderr})
-            else:
-                out["same_match_count_half_size"] = cnt == expected_matches
-        except Exception as e:  # reported, never required
-            out[key] = None
-            out["error"] = repr(e)[:300]
-    return out
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -533,7 +485,7 @@ def main():
     ap.add_argument("--size-gib", type=float, default=16.0)
     ap.add_argument("--patterns", type=int, default=1_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-experimental", action="store_true", help="skip the stride-2 leg (N=1, cfg5)")
+    ap.add_argument("--no-experimental", action="store_true", help="skip the other_workloads legs (N=1, cfg5)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")

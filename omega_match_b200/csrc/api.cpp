@@ -299,14 +299,8 @@ int olm_store_inspect(const char *compiled_file, olm_store_info_t *out) {
     olm::StagedStore s;
     olm::FilterBudget b;
     const std::string e2 = olm::stage_store(v, b, &s);
-    // (the second key table of the experimental stride-2 mode is staged and checked as well)
-    olm::StagedS2 s2;
     olm::StagedStats ss; // (and the tables of the exact statistics: everything create() stages)
-    if (e2.empty() && olm::check_staged_store(v, s) == 0 && olm::stage_store_s2(v, s, &s2).empty() &&
-        olm::check_staged_s2(v, s, s2) == 0 && olm::stage_stats(v, &ss).empty()) {
-      if (std::getenv("OLM_S2_DEBUG"))
-        std::fprintf(stderr, "libomega_match(b200): stride-2 table: K=%u run=%u keys=%u buckets=%zu recs=%zu\n",
-                     s2.params.key_bytes, s2.params.run, s2.n_keys, s2.keys.size(), s2.recs.size());
+    if (e2.empty() && olm::check_staged_store(v, s) == 0 && olm::stage_stats(v, &ss).empty()) {
       out->flags = v.hdr.flags;
       out->smallest = v.hdr.smallest;
       out->largest = v.hdr.largest;

@@ -106,27 +106,4 @@ struct DeviceStore {
   ByteClass cls;
 };
 
-// ---- experimental: stride-2 sampled probing (OLM_SAMPLE2=1 at create()) ----------
-// For stores whose patterns all have >= 6 bytes and start with a class run (cls.run >= 5), a second
-// key table holds TWO keys per pattern: the hash of pattern bytes [0, K) and of bytes [1, K+1),
-// K = min(8, shortest pattern - 1).  The scan then probes only the ODD positions p of a chunk:
-// an entry found with shift 0 is a candidate match starting at p, one with shift 1 a candidate
-// starting at p - 1, so every start position is still covered (odd starts by their own key,
-// even starts by the key one byte in) while only half of the positions are hashed and probed and
-// no on-chip bitmap is needed.  Slots and records have the layout of Slot / Rec above with w0/w1 =
-// the pattern bytes the PROBED position sees (bytes shift .. shift+7) and kS2Shift set in
-// Slot::meta (single) / Rec::len for shift-1 entries; records of a slot are ordered shift 1
-// first, then longest first: the order in which their matches (start p - 1, then start p) have
-// to leave the kernel.
-struct S2Store {
-  const uint4 *keys = nullptr;
-  const Slot *slots = nullptr;
-  const Rec *recs = nullptr;
-  uint32_t key_shift = 32, key_mask = 0, empty_key = 0;
-  uint32_t key_bytes = 0; // K (5..8); 0 = the mode is off
-  uint32_t tail_mask = 0; // as DeviceStore::tail_mask, for K
-  uint32_t run = 0;       // class run tested at a probed position: cls.run - 1 (4, 5 or 7)
-};
-constexpr uint32_t kS2Shift = 1u << 29; // pattern lengths stay below this when the mode is on
-
 } // namespace olm

@@ -97,10 +97,6 @@ struct EngineImpl {
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  // experimental stride-2 sampled mode (OLM_SAMPLE2=1 at create(); device_tables.h S2Store)
-  DevBuf d_s2keys, d_s2slots, d_s2recs;
-  S2Store s2;
-  ScanGeometry geo_s2;
   DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, misc, norm, map, windows, ghost, fscratch;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
@@ -175,29 +171,6 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && upload(impl->d_p23, staged.p23, &impl->ds.p23) == 0;
   ok = ok && upload(impl->d_set3, staged.set3, &impl->ds.set3) == 0;
   ok = ok && upload(impl->d_bitmap2, staged.bitmap2, &impl->ds.bitmap2) == 0;
-  if (const char *s2env = std::getenv("OLM_SAMPLE2"); s2env && s2env[0] == '1') {
-    // experimental, off by default: a second key table with two keys per pattern; launches without
-    // a position predicate then probe every second position only (scan.cu scan_chunk_s2)
-    StagedS2 t;
-    e = stage_store_s2(view, staged, &t);
-    if (e.empty() && check_staged_s2(view, staged, t) != 0) e = "internal error: stride-2 table failed its self check";
-    if (!e.empty()) {
-      delete eng;
-      return fail(e);
-    }
-    if (t.params.key_bytes) {
-      impl->s2 = t.params;
-      ok = ok && upload(impl->d_s2keys, t.keys, &impl->s2.keys) == 0;
-      ok = ok && upload(impl->d_s2slots, t.slots, &impl->s2.slots) == 0;
-      ok = ok && upload(impl->d_s2recs, t.recs, &impl->s2.recs) == 0;
-      impl->geo_s2 = scan_pick_geometry_s2(impl->smem_limit);
-      if (impl->geo_s2.stages == 0) impl->s2 = S2Store{};
-      if (std::getenv("OLM_S2_DEBUG"))
-        std::fprintf(stderr, "libomega_match(b200): stride-2 mode %s: K=%u run=%u keys=%u stages=%u cap=%u\n",
-                     impl->s2.key_bytes ? "on" : "off", t.params.key_bytes, t.params.run, t.n_keys, impl->geo_s2.stages,
-                     impl->geo_s2.chunk_cap);
-    }
-  }
   if (const char *sp = std::getenv("OLM_HOST_SPAN_BYTES")) {
     const unsigned long long v = std::strtoull(sp, nullptr, 10);
     impl->host_span = (v + kWindowBytes - 1) / kWindowBytes * kWindowBytes; // whole 4 MiB windows
@@ -266,7 +239,9 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   res->device = E.device;
   E.last = olm_cuda_timing_t{};
   std::memset(E.counters, 0, sizeof E.counters);
+  std::memset(E.stat_counters, 0, sizeof E.stat_counters);
   E.attempts_last = 0;
+  E.stats_valid = false; // (an empty range adds nothing to an attached stats struct, like the reference)
 
   const bool windowed = E.hdr.flags & kFlagAnyTransform;
   if (r.own_end < r.own_begin || r.own_end > r.global_size || r.own_begin < r.slice_begin ||
@@ -278,6 +253,17 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   if (windowed && ((r.own_begin % kWindowBytes) != 0)) {
     std::fprintf(stderr, "libomega_match(b200): shards of a transforming store must start on a 4 MiB window\n");
     return -1;
+  }
+  if (!windowed && r.own_end > r.own_begin) {
+    // the kernel reads one byte in front of the first owned position (start predicates; staged as a
+    // 16-byte front halo) and the longest pattern + 1 bytes behind the last one
+    const bool front_ok = r.own_begin == 0 || r.own_begin - r.slice_begin >= 16;
+    const uint64_t need_end = std::min<uint64_t>(r.global_size, r.own_end + E.hdr.largest + 1);
+    if (!front_ok || r.slice_begin + r.slice_len < need_end) {
+      std::fprintf(stderr, "libomega_match(b200): shard slice lacks its halo (16 bytes in front of own_begin, "
+                           "largest pattern + 1 bytes behind own_end)\n");
+      return -1;
+    }
   }
   const uint64_t n_own = r.own_end - r.own_begin;
   if (n_own == 0) return 0;
@@ -366,9 +352,6 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.flags = fl;
     P.stages = E.geo.stages;
     P.chunk_cap = E.geo.chunk_cap;
-    P.s2 = E.s2;
-    P.s2_stages = E.geo_s2.stages;
-    P.s2_chunk_cap = E.geo_s2.chunk_cap;
     P.tail_byte = 0;
 
     if (!windowed) {
@@ -608,7 +591,13 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   if (!results) return nullptr;
   results->count = 0;
   results->matches = static_cast<omega_match_result_t *>(std::malloc(sizeof(omega_match_result_t)));
-  if (n == 0 || !haystack) return results;
+  if (n == 0 || !haystack) { // nothing scanned: collect_stats() must not add the previous call's counters again
+    std::memset(E.counters, 0, sizeof E.counters);
+    std::memset(E.stat_counters, 0, sizeof E.stat_counters);
+    E.attempts_last = 0;
+    E.stats_valid = false;
+    return results;
+  }
   auto bail = [&]() -> omega_match_results_t * {
     if (!pinned_result_release(results->matches)) std::free(results->matches);
     std::free(results);
@@ -651,6 +640,9 @@ int64_t Engine::no_overlap_inplace(void *dev_records, uint64_t count) {
   EngineImpl &E = *impl_;
   OLM_CUDA(cudaSetDevice(E.device));
   if (count < 2) return (int64_t)count;
+  // the records may have been produced on any stream of the caller (a gather, a copy): the
+  // matcher's stream is non-blocking and would not wait for them (same contract as match_device)
+  OLM_CUDA(cudaDeviceSynchronize());
   if (E.out2.ensure(count * sizeof(Record))) return -1;
   if (E.fscratch.ensure(filter_scratch_bytes(count))) return -1;
   if (E.misc.ensure(size_t(kMaxBatches) * 8 + 256)) return -1;
@@ -671,6 +663,7 @@ int Engine::sort_records(void *dev_records, uint64_t count) {
   EngineImpl &E = *impl_;
   OLM_CUDA(cudaSetDevice(E.device));
   if (count < 2) return 0;
+  OLM_CUDA(cudaDeviceSynchronize()); // see no_overlap_inplace
   if (E.out2.ensure(count * sizeof(Record))) return -1;
   if (E.fscratch.ensure(sort_scratch_bytes(count))) return -1;
   uint32_t launches = 0;

@@ -519,33 +519,6 @@ struct Scanner {
     a &= a >> (c.run - 4);
     return a & 0xFFFFu;
   }
-  // the same with the run length given (stride-2 mode: run = cls.run - 1, i.e. 4, 5 or 7)
-  __device__ __forceinline__ uint32_t class_runs16_run(const uint4 &v, const uint2 &nx, uint32_t run) const {
-    const ByteClass &c = P.st.cls;
-    const uint32_t w[6] = {v.x, v.y, v.z, v.w, nx.x, nx.y};
-    const uint32_t and4 = c.and4, lo0 = c.addlo[0], hi0 = c.addhi[0];
-    uint32_t a = 0;
-    if (c.n_ranges > 1) { // (uniform branch: one block of straight-line code per case)
-      const uint32_t lo1 = c.addlo[1], hi1 = c.addhi[1];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const uint32_t t = w[i] & and4;
-        const uint32_t in = ((t + lo0) & ~(t + hi0)) | ((t + lo1) & ~(t + hi1));
-        a |= gather4(in & ~w[i] & 0x80808080u) << (4 * i);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const uint32_t t = w[i] & and4;
-        a |= gather4((t + lo0) & ~(t + hi0) & ~w[i] & 0x80808080u) << (4 * i);
-      }
-    }
-    a &= a >> 1;
-    a &= a >> 2;
-    a &= a >> (run - 4);
-    return a & 0xFFFFu;
-  }
-
   // stage 1 for one lane: 16 positions -> candidate masks (bit k = position lpos + k)
   __device__ __forceinline__ void stage1(const TileCtx &T, uint32_t lpos, uint32_t &cg, uint32_t &cp) const {
     const uint32_t src = T.sb32 + kTilePre + lpos;
@@ -895,221 +868,6 @@ struct Scanner {
     return found;
   }
 
-  // ================= experimental: stride-2 sampled mode (device_tables.h S2Store) =================
-  // A probed position p (odd) stands for the start positions p - 1 (entries with shift 1) and p
-  // (shift 0).  The slot's entries come in the order their matches leave the kernel: shift 1
-  // longest first, then shift 0 longest first.  `emit(start, len)` once per accepted match.
-  template <typename Emit>
-  __device__ __forceinline__ void verify_s2(const TileCtx &T, uint32_t p, uint32_t slot, Emit &&emit) const {
-    const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.s2.slots + slot));
-    const uint32_t meta = s.z;
-    if (meta == 0) return; // the position's key equals empty_key and met an unused place
-    const uint32_t q = T.sb32 + kTilePre + p;
-    const unsigned long long hay = ((unsigned long long)lds_le32(q + 4) << 32) | lds_le32(q);
-    const uint32_t prev = lds8(q - 1); // p is odd, hence >= 1
-    const uint32_t rem = T.rem0 - p;
-    const bool longest = fl & kLongestOnly;
-    n_hits += stat_inc;
-    n_long_hits += stat_inc;
-    uint32_t done = 0; // bit sh: a match of this shift has been emitted
-    auto entry = [&](uint32_t w0, uint32_t w1, uint32_t lenf, uint32_t store_off) {
-      const uint32_t sh = (lenf >> 29) & 1u, len = lenf & (kS2Shift - 1u);
-      const uint32_t body = len - sh; // pattern bytes from p on (>= key_bytes)
-      // the start is not one of this tile's positions / the pattern does not fit (matcher.c:203)
-      if (p - sh >= T.nscan || body > rem) return;
-      if (longest && ((done >> sh) & 1u)) return;
-      n_cmp += stat_inc;
-      const uint32_t drop = body >= 8 ? 0u : (8u - body) * 8u;
-      if (((hay ^ (((unsigned long long)w1 << 32) | w0)) << drop) != 0) return;
-      const uint8_t *pat = P.st.store + store_off;
-      if (sh && prev != __ldg(pat)) return;
-      for (uint32_t i = 8; i < body; ++i)
-        if (hay_byte(T, p + i) != __ldg(pat + sh + i)) return;
-      emit(p - sh, len);
-      done |= 1u << sh;
-    };
-    if (meta & kSlotMulti) {
-      const uint32_t cnt = meta & kSlotValueMask;
-      for (uint32_t j = 0; j < cnt; ++j) {
-        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.s2.recs + s.w + j));
-        entry(r.x, r.w, r.y, r.z);
-      }
-    } else {
-      entry(s.x, s.y, meta, s.w);
-    }
-  }
-
-  // verify_batch for the sampled mode: up to 32 entries {p, slot} of Q2, matches staged in entry
-  // order as packed (start, len) -- the layout place_kernel reads.
-  __device__ __forceinline__ uint32_t verify_batch_s2(const TileCtx &T, uint32_t q2, uint32_t n, uint32_t lane,
-                                                      uint32_t stage, uint32_t used, uint32_t cap,
-                                                      uint32_t *overflow) const {
-    bool mine = lane < n;
-    const unsigned long long ent = mine ? lds64u(q2 + 8u * lane) : 0ull;
-    const uint32_t slot = (uint32_t)ent, p = (uint32_t)(ent >> 32);
-    uint32_t at = 0, tot = 0, skip = 0;
-    const uint32_t keep = stat_inc;
-    bool again;
-    do {
-      uint32_t cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-      if (mine)
-        verify_s2(T, p, slot, [&](uint32_t start, uint32_t len) {
-          if (len >> kPackLenBits) *overflow = 1; // (the chunk is evaluated again by redo_kernel)
-          const uint32_t e = (start << kPackLenBits) | len;
-          const uint32_t j = cnt - skip; // wraps to a huge value while cnt < skip
-          if (j == 0) m0 = e;
-          else if (j == 1) m1 = e;
-          else if (j == 2) m2 = e;
-          else if (j == 3) m3 = e;
-          ++cnt;
-        });
-      if (skip == 0) {
-        const uint32_t bal = __ballot_sync(kFull, cnt > 0);
-        if (!bal) return 0;
-        uint32_t pre;
-        if (!__any_sync(kFull, cnt > 1)) {
-          pre = __popc(bal & ((1u << lane) - 1u));
-          tot = __popc(bal);
-        } else {
-          uint32_t in2 = cnt;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, in2, d);
-            if (lane >= (uint32_t)d) in2 += t;
-          }
-          pre = in2 - cnt;
-          tot = __shfl_sync(kFull, in2, 31);
-        }
-        at = used + pre;
-      }
-      auto put = [&](uint32_t i, uint32_t e) {
-        if (at + i < cap)
-          sts32(stage + 4u * (at + i), e);
-        else
-          *overflow = 1;
-      };
-      if (cnt > skip) put(skip, m0);
-      if (cnt > skip + 1) put(skip + 1, m1);
-      if (cnt > skip + 2) put(skip + 2, m2);
-      if (cnt > skip + 3) put(skip + 3, m3);
-      skip += 4;
-      stat_inc = 0;
-      mine = mine && cnt > skip;
-      again = __any_sync(kFull, mine);
-    } while (again);
-    stat_inc = keep;
-    return tot;
-  }
-
-  // One 512-byte chunk in the sampled mode: class test of the ODD positions in registers -> Q1 ->
-  // one key probe per survivor (no bitmap) -> Q2 -> verify_batch_s2.  Exact match count of the
-  // chunk; the matches are staged at `stage` (kStageMode only: an overflowing chunk is redone by
-  // redo_kernel through the regular tables).
-  __device__ __forceinline__ uint32_t scan_chunk_s2(const TileCtx &T, uint32_t sb_off, uint32_t q1_off,
-                                                    uint32_t q2_off, uint32_t cbase, uint32_t lane, uint32_t stage,
-                                                    uint32_t cap, uint32_t *overflow) const {
-    const uint32_t lpos = cbase + lane * 16; // a multiple of 16: odd k <=> odd position
-    const uint32_t src = sb_off + kTilePre + lpos;
-    const uint4 v = lds128(src);
-    uint32_t cand = class_runs16_run(v, lds64(src + 16), P.s2.run) & 0xAAAAu;
-    // positions p <= nscan: p == nscan (odd) still stands for the start nscan - 1
-    if (lpos + 16 > T.nscan) cand &= lpos > T.nscan ? 0u : ((2u << (T.nscan - lpos)) - 1u);
-    const uint32_t cnt = __popc(cand);
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, incl, d);
-      if (lane >= (uint32_t)d) incl += t;
-    }
-    const uint32_t total = __shfl_sync(kFull, incl, 31);
-    if (total == 0) return 0;
-    {
-      uint32_t qa = q1_off + 2u * (incl - cnt);
-      const uint32_t eb = lane * 16;
-      if (__any_sync(kFull, cnt > 2)) { // dense: 8 predicated steps, no branches
-#pragma unroll
-        for (int k = 1; k < 16; k += 2)
-          if ((cand >> k) & 1u) {
-            sts16(qa, eb + k);
-            qa += 2;
-          }
-      } else {
-        while (cand) {
-          const uint32_t k = __ffs(cand) - 1;
-          sts16(qa, eb + k);
-          cand &= cand - 1;
-          qa += 2;
-        }
-      }
-    }
-    __syncwarp();
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t tile_off = sb_off + kTilePre + cbase;
-    const uint32_t key_shift = P.s2.key_shift, empty = P.s2.empty_key, key_mask = P.s2.key_mask;
-    const uint4 *keys = P.s2.keys;
-    const uint32_t rem_c = T.rem0 - cbase; // >= 1
-    const uint32_t tmask = P.s2.tail_mask, kbytes = P.s2.key_bytes;
-    const bool near_end = rem_c < (uint32_t)kChunkBytes + 8u;
-    uint32_t found = 0, q2n = 0;
-    constexpr int U = 2;
-    for (uint32_t base = 0; base < total; base += 32 * U) {
-      uint32_t e[U], key[U], bucket[U];
-      bool pass[U];
-      uint4 kb[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const uint32_t idx = base + u * 32 + lane;
-        pass[u] = idx < total;
-        e[u] = pass[u] ? lds16(q1_off + 2u * idx) : 1u;
-        const uint32_t a = tile_off + e[u], a4 = a & ~3u, sh8 = a << 3;
-        const uint32_t x0 = lds32(a4), x1 = lds32(a4 + 4), x2 = lds32(a4 + 8);
-        key[u] = (__byte_perm(__funnelshift_r(x0, x1, sh8), 0, 0x0123) * kHashMul) ^
-                 ((__funnelshift_r(x1, x2, sh8) & tmask) * kHashMul2);
-        if (near_end) pass[u] = pass[u] && (e[u] + kbytes <= rem_c); // only the segment's last chunks
-        bucket[u] = key[u] >> key_shift;
-        if (pass[u]) kb[u] = ld_keys(keys + bucket[u]); // (not read when !pass[u])
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u > 0 && base + u * 32 >= total) break;
-        const uint32_t g = key[u];
-        bool hit = pass[u] && (kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g);
-        const bool more = pass[u] && !hit && kb[u].w != empty; // rare: full home bucket without the key
-        if (!__any_sync(kFull, hit || more)) continue;            // the usual end of a round
-        if (__any_sync(kFull, more)) {
-          while (pass[u] && !hit && kb[u].w != empty) {
-            bucket[u] = (bucket[u] + 1) & key_mask;
-            kb[u] = ld_keys(keys + bucket[u]);
-            hit = kb[u].x == g || kb[u].y == g || kb[u].z == g || kb[u].w == g;
-          }
-        }
-        const uint32_t bal = __ballot_sync(kFull, hit);
-        if (!bal) continue;
-        const uint32_t place = kb[u].y == g ? 1u : kb[u].z == g ? 2u : kb[u].w == g ? 3u : 0u;
-        if (hit)
-          sts64u(q2_off + 8u * (q2n + __popc(bal & lt)),
-                 ((unsigned long long)(cbase + e[u]) << 32) | (4u * bucket[u] + place));
-        q2n += __popc(bal);
-      }
-      __syncwarp();
-      const bool last = base + 32 * U >= total;
-      while (q2n >= 32 || (last && q2n)) {
-        const uint32_t nb = q2n < 32 ? q2n : 32;
-        found += verify_batch_s2(T, q2_off, nb, lane, stage, found, cap, overflow);
-        const uint32_t rest = q2n - nb; // <= 63
-        const unsigned long long mv0 = lane < rest ? lds64u(q2_off + 8u * (32 + lane)) : 0ull;
-        const unsigned long long mv1 = 32 + lane < rest ? lds64u(q2_off + 8u * (64 + lane)) : 0ull;
-        __syncwarp();
-        if (lane < rest) sts64u(q2_off + 8u * lane, mv0);
-        if (32 + lane < rest) sts64u(q2_off + 8u * (32 + lane), mv1);
-        __syncwarp();
-        q2n = rest;
-      }
-    }
-    __syncwarp();
-    return found;
-  }
-
   __device__ __forceinline__ void write_record(unsigned long long r, unsigned long long emit_base,
                                                unsigned long long pos, uint32_t len, const uint32_t *map) const {
     put_record(P, r, emit_base, pos, len, map);
@@ -1233,18 +991,16 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
-// S2: the experimental stride-2 sampled mode (scan_chunk_s2) -- no filter in shared memory, its own
-// ring depth and staging capacity.
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool S2 = false>
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t S = S2 ? P.s2_stages : P.stages, cap = S2 ? P.s2_chunk_cap : P.chunk_cap;
-  const SmemLayout L = carve<HAS_G4 && !S2, HAS_P23>(smem, P, S, kScanWarps * cap);
+  const uint32_t S = P.stages, cap = P.chunk_cap;
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, kScanWarps * cap);
   SmemHeader &H = *L.H;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  load_filters<HAS_G4 && !S2, HAS_P23>(L, P, tid, kScanThreads);
+  load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
   if (tid == 0) {
     for (uint32_t s = 0; s < kMaxStages; ++s) {
       mbar_init(&H.full[s], 1);
@@ -1368,9 +1124,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     const uint32_t cbase = ci * kChunkBytes;
     uint32_t n = 0, ovf = 0;
     if (cbase < T.nscan) {
-      if (S2)
-        n = sc.scan_chunk_s2(T, T.sb32, q1_32, q2_32, cbase, lane, stage32, cap, &ovf);
-      else if (FAST)
+      if (FAST)
         n = sc.template scan_chunk_fast<kStageMode>(T, T.sb32, g4_32, p23_32, q1_32, q2_32, cbase, lane, stage32, cap, 0,
                                                     0, nullptr, &ovf);
       else
@@ -1588,22 +1342,13 @@ __global__ void __launch_bounds__(kPrefixThreads) place_kernel(const __grid_cons
   }
 }
 
-size_t scan_smem_bytes_s2(uint32_t stages, uint32_t chunk_cap) {
-  return kSmemHeader + size_t(stages) * kStageBytes + kQ2Bytes + size_t(kScanWarps) * chunk_cap * 4 + kQ1Bytes;
-}
-
 template <bool G, bool Q, bool C>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
   const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
   // the lean per-candidate path covers every store, as long as no position predicate is requested
   constexpr bool can_fast = G || Q;
   const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
-  bool s2 = false;
-  if constexpr (G && !Q && C) s2 = fast && p.s2.key_bytes != 0 && p.s2_stages != 0;
-  if (s2) {
-    if constexpr (G && !Q && C)
-      scan_kernel<G, Q, C, true, true><<<grid, kScanThreads, scan_smem_bytes_s2(p.s2_stages, p.s2_chunk_cap), stream>>>(p);
-  } else if (fast)
+  if (fast)
     scan_kernel<G, Q, C, can_fast><<<grid, kScanThreads, smem, stream>>>(p);
   else
     scan_kernel<G, Q, C, false><<<grid, kScanThreads, smem, stream>>>(p);
@@ -1629,10 +1374,6 @@ cudaError_t configure_variant(size_t smem_limit) {
     e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     if (e != cudaSuccess) return e;
   }
-  if constexpr (G && !Q && C) {
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
-    if (e != cudaSuccess) return e;
-  }
   return cudaFuncSetAttribute(redo_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
 }
 
@@ -1651,20 +1392,6 @@ ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
   for (uint32_t s = kMaxStages; s >= 2; --s) {
     if (scan_smem_bytes(st, s, kChunkCapMin) > smem_limit) continue;
     const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
-    uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
-    if (cap > kChunkCapMax) cap = kChunkCapMax;
-    g.stages = s;
-    g.chunk_cap = cap;
-    return g;
-  }
-  return g;
-}
-
-ScanGeometry scan_pick_geometry_s2(size_t smem_limit) {
-  ScanGeometry g;
-  for (uint32_t s = kMaxStages; s >= 2; --s) {
-    if (scan_smem_bytes_s2(s, kChunkCapMin) > smem_limit) continue;
-    const size_t spare = smem_limit - scan_smem_bytes_s2(s, 0);
     uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
     if (cap > kChunkCapMax) cap = kChunkCapMax;
     g.stages = s;

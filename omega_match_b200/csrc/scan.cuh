@@ -101,10 +101,6 @@ struct ScanParams {
   uint32_t flags;
   uint32_t stages;    // ring depth
   uint32_t chunk_cap; // staged matches per chunk
-  // experimental stride-2 sampled mode (device_tables.h S2Store; s2.key_bytes == 0: off).  Appended
-  // here so that nothing above moves.
-  S2Store s2;
-  uint32_t s2_stages, s2_chunk_cap; // geometry of scan_kernel in that mode (no filter in shared memory)
 };
 
 // One per 512-byte chunk, written by the warp that scanned it.
@@ -125,7 +121,6 @@ size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_ca
 // chooses ring depth and staging capacity for the shared memory there is; stages == 0 if the
 // filters do not fit at all
 ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit);
-ScanGeometry scan_pick_geometry_s2(size_t smem_limit); // stride-2 mode: the ring and the queues only
 // scan -> prefix over the chunk counts (two kernels) -> placement of the records in final order
 // -> redo pass (exits at once when no chunk overflowed)
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches);

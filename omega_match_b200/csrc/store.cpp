@@ -45,7 +45,7 @@ std::string parse_store(const uint8_t *f, size_t size, StoreView *v) {
   v->size = size;
 
   uint64_t off = kHeaderBytes;
-  auto need = [&](uint64_t n) { return off + n <= size; };
+  auto need = [&](uint64_t n) { return off <= size && n <= size - off; }; // (no wrap-around for huge n)
   if (!need(h.store_bytes)) return "pattern store runs past the end of the file";
   v->patterns = f + off;
   off += h.store_bytes;
@@ -64,7 +64,7 @@ std::string parse_store(const uint8_t *f, size_t size, StoreView *v) {
   if (!need(h.blob_bytes)) return "bucket data runs past the end of the file";
   v->blob = f + off;
   off += h.blob_bytes;
-  if (off + h.short_bytes != size) return "short matcher size mismatch"; // matcher.c:425
+  if (off > size || h.short_bytes != size - off) return "short matcher size mismatch"; // matcher.c:425
   if (h.short_bytes) {
     if (h.short_bytes < 8 + 32 + 8192 + 16 || std::memcmp(f + off, kMagicShort, 8) != 0)
       return "short matcher magic mismatch";
@@ -118,7 +118,7 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     for (uint32_t j = 0; j < b.count; ++j) {
       const uint64_t po = rd64(b.recs + 16ull * j);
       const uint32_t pl = rd32(b.recs + 16ull * j + 8);
-      if (pl < 5 || pl > kSlotValueMask || po + pl > h.store_bytes) return "pattern record out of range";
+      if (pl < 5 || pl > kSlotValueMask || po > h.store_bytes || pl > h.store_bytes - po) return "pattern record out of range";
       if (rd32(v.patterns + po) != __builtin_bswap32(b.gram)) return "pattern does not start with its bucket gram";
     }
     n_long += b.count;
@@ -442,176 +442,6 @@ std::string stage_stats(const StoreView &v, StagedStats *s) {
   }
   if (s->lens.empty()) s->lens.push_back(0);
   return "";
-}
-
-// ---- stride-2 sampled mode (device_tables.h S2Store) ---------------------------------------------
-#ifndef OLM_S2_KEY_EXTRA_LOG2
-#define OLM_S2_KEY_EXTRA_LOG2 1
-#endif
-namespace {
-struct S2Entry {
-  uint32_t key, shift, len;
-  uint64_t off;
-};
-// little-endian word of pattern bytes [from, from + 4), zero padded past the pattern's end
-uint32_t pat_word(const StoreView &v, uint64_t po, uint32_t pl, uint32_t from) {
-  uint32_t w = 0;
-  for (uint32_t i = 0; i < 4 && from + i < pl; ++i) w |= uint32_t(v.patterns[po + from + i]) << (8 * i);
-  return w;
-}
-uint32_t s2_key(const StoreView &v, const S2Store &d, uint64_t po, uint32_t pl, uint32_t shift) {
-  return key_hash(__builtin_bswap32(pat_word(v, po, pl, shift)), pat_word(v, po, pl, shift + 4) & d.tail_mask);
-}
-} // namespace
-
-std::string stage_store_s2(const StoreView &v, const StagedStore &s, StagedS2 *t) {
-  *t = StagedS2{};
-  const Header &h = v.hdr;
-  if (v.n1 || v.n2 || v.n3 || v.n4 || h.blob_bytes == 0 || s.params.cls.run < 5) return "";
-  // (the blob was validated by stage_store)
-  uint32_t min_long = 0xFFFFFFFFu, max_long = 0;
-  uint64_t n_long = 0;
-  for (uint64_t p = 0; p < h.blob_bytes;) {
-    const uint32_t count = rd32(v.blob + p + 4);
-    for (uint32_t j = 0; j < count; ++j) {
-      const uint32_t pl = rd32(v.blob + p + 8 + 16ull * j + 8);
-      min_long = std::min(min_long, pl);
-      max_long = std::max(max_long, pl);
-    }
-    n_long += count;
-    p += 8 + uint64_t(count) * kBucketRecordBytes;
-  }
-  if (min_long < 6 || max_long >= kS2Shift || n_long * 2 > kSlotValueMask) return "";
-  S2Store &d = t->params;
-  const uint32_t K = std::min<uint32_t>(8, min_long - 1);
-  d.tail_mask = K >= 8 ? 0xFFFFFFFFu : ((1u << (8 * (K - 4))) - 1u);
-  d.run = s.params.cls.run - 1;
-
-  std::vector<S2Entry> ents;
-  ents.reserve(size_t(n_long) * 2);
-  for (uint64_t p = 0; p < h.blob_bytes;) {
-    const uint32_t count = rd32(v.blob + p + 4);
-    for (uint32_t j = 0; j < count; ++j) {
-      const uint64_t po = rd64(v.blob + p + 8 + 16ull * j);
-      const uint32_t pl = rd32(v.blob + p + 8 + 16ull * j + 8);
-      for (uint32_t shift = 0; shift < 2; ++shift) ents.push_back(S2Entry{s2_key(v, d, po, pl, shift), shift, pl, po});
-    }
-    p += 8 + uint64_t(count) * kBucketRecordBytes;
-  }
-  std::vector<uint32_t> all;
-  all.reserve(ents.size());
-  for (const S2Entry &e : ents) all.push_back(e.key);
-  std::sort(all.begin(), all.end());
-  all.erase(std::unique(all.begin(), all.end()), all.end());
-  // (experiment knob: OLM_S2_KEY_EXTRA_LOG2=0 in the environment halves the table -- 32 MiB at load
-  // <= 0.25 instead of 64 MiB at <= 0.125 for 2 M keys -- without a rebuild)
-  uint32_t extra = OLM_S2_KEY_EXTRA_LOG2;
-  if (const char *e = std::getenv("OLM_S2_KEY_EXTRA_LOG2"); e && e[0] >= '0' && e[0] <= '2' && !e[1]) extra = uint32_t(e[0] - '0');
-  const uint32_t lg_buckets = std::max<uint32_t>(3, ceil_log2(std::max<uint64_t>(1, all.size())) + extra);
-  if (lg_buckets > 27) return "";
-  const uint32_t n_buckets = 1u << lg_buckets;
-  d.key_shift = 32 - lg_buckets;
-  d.key_mask = n_buckets - 1;
-  {
-    uint32_t e = 0xFFFFFFFFu;
-    while (std::binary_search(all.begin(), all.end(), e)) --e;
-    d.empty_key = e;
-  }
-  t->keys.assign(n_buckets, make_uint4(d.empty_key, d.empty_key, d.empty_key, d.empty_key));
-  t->slots.assign(size_t(n_buckets) * 4, Slot{0, 0, 0, 0});
-  // entries grouped by slot: sort by (slot, shift descending, length descending)
-  std::vector<size_t> slot_of(ents.size());
-  for (size_t i = 0; i < ents.size(); ++i) {
-    const uint32_t key = ents[i].key;
-    for (uint32_t b = key >> d.key_shift;; b = (b + 1) & d.key_mask) {
-      uint32_t *k = reinterpret_cast<uint32_t *>(&t->keys[b]);
-      uint32_t j = 0;
-      while (j < 4 && k[j] != key && k[j] != d.empty_key) ++j;
-      if (j < 4) {
-        k[j] = key;
-        slot_of[i] = 4 * size_t(b) + j;
-        break;
-      }
-    }
-  }
-  std::vector<uint32_t> order(ents.size());
-  for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-    if (slot_of[a] != slot_of[b]) return slot_of[a] < slot_of[b];
-    if (ents[a].shift != ents[b].shift) return ents[a].shift > ents[b].shift;
-    return ents[a].len > ents[b].len;
-  });
-  for (size_t i = 0; i < order.size();) {
-    size_t j = i;
-    while (j < order.size() && slot_of[order[j]] == slot_of[order[i]]) ++j;
-    Slot &sl = t->slots[slot_of[order[i]]];
-    auto rec_of = [&](const S2Entry &e) {
-      return Rec{pat_word(v, e.off, e.len, e.shift), e.len | (e.shift ? kS2Shift : 0u), uint32_t(e.off),
-                 pat_word(v, e.off, e.len, e.shift + 4)};
-    };
-    if (j - i == 1) {
-      const Rec r = rec_of(ents[order[i]]);
-      sl = Slot{r.w0, r.w1, r.len, r.store_off};
-    } else {
-      sl = Slot{0, 0, kSlotMulti | uint32_t(j - i), uint32_t(t->recs.size())};
-      for (size_t q = i; q < j; ++q) t->recs.push_back(rec_of(ents[order[q]]));
-    }
-    i = j;
-  }
-  if (t->recs.empty()) t->recs.push_back(Rec{0, 0, 0, 0});
-  t->n_keys = uint32_t(all.size());
-  d.key_bytes = K; // the mode is on
-  return "";
-}
-
-uint64_t check_staged_s2(const StoreView &v, const StagedStore &s, const StagedS2 &t) {
-  const S2Store &d = t.params;
-  if (d.key_bytes == 0) return 0;
-  uint64_t bad = 0;
-  auto probe = [&](uint32_t key) -> const Slot * { // the probe of scan_chunk_s2
-    for (uint32_t b = key >> d.key_shift;; b = (b + 1) & d.key_mask) {
-      const uint32_t *k = reinterpret_cast<const uint32_t *>(&t.keys[b]);
-      for (uint32_t j = 0; j < 4; ++j)
-        if (k[j] == key) return key == d.empty_key ? nullptr : &t.slots[4 * size_t(b) + j];
-      if (k[3] == d.empty_key) return nullptr;
-    }
-  };
-  for (uint64_t p = 0; p < v.hdr.blob_bytes;) {
-    const uint32_t count = rd32(v.blob + p + 4);
-    for (uint32_t j = 0; j < count; ++j) {
-      const uint64_t po = rd64(v.blob + p + 8 + 16ull * j);
-      const uint32_t pl = rd32(v.blob + p + 8 + 16ull * j + 8);
-      for (uint32_t shift = 0; shift < 2; ++shift) {
-        // what the kernel tests before it probes: `run` class bytes from the probed position on,
-        // key_bytes bytes left; then the entry with exactly these fields must be listed
-        bool ok = pl >= d.key_bytes + shift;
-        for (uint32_t i = 0; i < d.run; ++i) ok = ok && class_has(s.params.cls, v.patterns[po + shift + i]);
-        const Slot *sl = ok ? probe(s2_key(v, d, po, pl, shift)) : nullptr;
-        ok = sl != nullptr;
-        const uint32_t lenf = pl | (shift ? kS2Shift : 0u);
-        const uint32_t w0 = pat_word(v, po, pl, shift), w1 = pat_word(v, po, pl, shift + 4);
-        if (ok && !(sl->meta & kSlotMulti)) {
-          ok = sl->meta == lenf && sl->ref == po && sl->w0 == w0 && sl->w1 == w1;
-        } else if (ok) {
-          const uint32_t n = sl->meta & kSlotValueMask;
-          bool found = false;
-          for (uint32_t q = 0; q < n; ++q) {
-            const Rec &rc = t.recs[sl->ref + q];
-            if (q > 0) { // shift 1 first, then longest first
-              const Rec &pr = t.recs[sl->ref + q - 1];
-              const uint32_t sa = pr.len & kS2Shift, sb = rc.len & kS2Shift;
-              if (sa < sb || (sa == sb && (pr.len & ~kS2Shift) < (rc.len & ~kS2Shift))) ok = false;
-            }
-            if (rc.len == lenf && rc.store_off == po) found = rc.w0 == w0 && rc.w1 == w1;
-          }
-          ok = ok && found;
-        }
-        bad += !ok;
-      }
-    }
-    p += 8 + 16ull * count;
-  }
-  return bad;
 }
 
 uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {

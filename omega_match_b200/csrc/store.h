@@ -50,19 +50,6 @@ struct FilterBudget {
 
 std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedStore *out);
 
-// Host image of the second key table of the stride-2 sampled mode (device_tables.h S2Store);
-// params.key_bytes == 0 when the store does not qualify.  `s` = the store's regular staging.
-struct StagedS2 {
-  std::vector<uint4> keys;
-  std::vector<Slot> slots;
-  std::vector<Rec> recs;
-  S2Store params; // pointer members are filled in after upload
-  uint32_t n_keys = 0;
-};
-std::string stage_store_s2(const StoreView &v, const StagedStore &s, StagedS2 *out);
-// every (pattern, shift) is found again through the probe the S2 kernel uses; 0 = sound
-uint64_t check_staged_s2(const StoreView &v, const StagedStore &s, const StagedS2 &t);
-
 // Host image of the tables behind the exact statistics (stats.cuh): the file's Bloom bits as
 // 64-bit words, its gram -> bucket map as an open-addressing table, the pattern lengths per bucket.
 struct StagedStats {

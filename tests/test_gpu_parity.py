@@ -717,18 +717,3 @@ def test_key_collisions_between_different_prefixes(store_cache, k):
         check(m, o, hay, word_boundary=True)
         assert got.size >= 50 * 8 and shortest >= k
 
-
-def test_experimental_stride2_scan_quick_parity():
-    """The stride-2 sampled scan (OLM_SAMPLE2=1; off by default) against the
-    oracle: buffer / chunk / tile edges, keys that coincide for both shifts, a dense run whose
-    staging area overflows (redo_kernel), a case-folding store, with and without longest_only /
-    no_overlap.  Runs `tests/gpu_s2_check.py --quick` in a process of its own (the mode is chosen
-    at create() from the environment) -- the command that ran green on a B200 in round 1
-    (profiles/r1_s2_quick_parity.log)."""
-    import subprocess
-    import sys
-    script = str(inputs.GOLDEN.parent / "gpu_s2_check.py")
-    r = subprocess.run([sys.executable, script, "--quick"], env=dict(os.environ, OLM_SAMPLE2="1", OLM_S2_DEBUG="1"),
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "TOTAL BAD 0" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
-    assert "stride-2 mode on" in r.stderr  # the mode really was engaged
