@@ -167,12 +167,14 @@ typedef struct {
 
 /* Environment variables read at omega_list_matcher_create():
  *   OLM_CUDA_DEVICE=<i>       default GPU (see olm_cuda_set_default_device)
+ *   OLM_CUDA_DEVICES=<list>   "0,1,2,3", "0-7" or "all": the matcher owns one engine per listed GPU
+ *                             and omega_list_matcher_match() shards every host haystack by byte
+ *                             range over them (see olm_cuda_matcher_create_multi)
  *   OLM_EXACT_STATS=1         see olm_cuda_set_exact_stats
- *   OLM_SAMPLE2=1             EXPERIMENTAL, off by default: stride-2 sampled scan for stores whose
- *                             patterns all have >= 6 bytes (same results)
- *   OLM_HOST_SPAN_BYTES=<n>   EXPERIMENTAL, off by default: omega_list_matcher_match scans host
- *                             haystacks longer than n bytes in spans of n bytes (bounded device
- *                             memory; same results) */
+ *   OLM_HOST_SPAN_BYTES=<n>   omega_list_matcher_match scans host haystacks longer than n bytes in
+ *                             spans of n bytes (bounded device memory; same results)
+ *   OLM_PRIV=0                plain stores: scan chunks in the staged tile instead of a private
+ *                             copy per warp (a tuning knob; same results) */
 int olm_cuda_device_count(void);
 /* Choose the GPU a matcher lives on BEFORE create (process wide default: device 0 or
  * $OLM_CUDA_DEVICE). */
@@ -212,8 +214,48 @@ int olm_cuda_match_shard_host(const omega_list_matcher_t *matcher, const void *h
                               int longest_only, int word_boundary, int word_prefix, int word_suffix,
                               int line_start, int line_end, olm_cuda_results_t *out);
 
+/* ---- several GPUs ------------------------------------------------------------------
+ * (1) One process, N GPUs.  The matcher owns one engine per GPU; omega_list_matcher_match() on it
+ * shards the host haystack by byte range (ownership rule: a match belongs to the shard that owns
+ * its start; stores with a transform flag shard on 4 MiB windows), runs every shard on its GPU
+ * from its own host thread (H2D over that GPU's link overlapped with its scan), and delivers ONE
+ * result array in final order: the records are copied out by all GPUs at once, each into its
+ * range of the array; with no_overlap they are first gathered on the first GPU over NVLink and
+ * filtered there.  The olm_cuda_* device entry points of such a matcher address its first GPU. */
+omega_list_matcher_t *olm_cuda_matcher_create_multi(const char *compiled_file, const int *devices,
+                                                    int n_devices);
+int olm_cuda_matcher_device_count(const omega_list_matcher_t *matcher);
+
+/* The byte range rank `rank` of `world` owns and the bytes it has to hold (its slice: 16 bytes in
+ * front, the longest pattern + 1 behind; none for stores with a transform flag, which shard on
+ * 4 MiB windows).  olm_shard_plan() needs no GPU (largest pattern length and transform flags as
+ * olm_store_inspect() reports them). */
+typedef struct {
+  uint64_t own_begin, own_end, slice_begin, slice_end;
+} olm_shard_t;
+int olm_shard_plan(uint32_t largest_pattern, int windowed, uint64_t global_size, int world, int rank,
+                   olm_shard_t *out);
+int olm_cuda_shard_plan(const omega_list_matcher_t *matcher, uint64_t global_size, int world, int rank,
+                        olm_shard_t *out);
+
+/* (2) One process per GPU.  Every rank scans its shard (olm_cuda_match_shard[_host]) and the ranks
+ * gather the per-rank sorted records on `root` with NCCL over NVLink: counts by ncclAllGather, the
+ * records by one group of ncclSend/ncclRecv into the root matcher's memory in rank order (= global
+ * order), then -- if asked -- the no_overlap filter once on the whole.  Rank 0 makes the id
+ * (128 bytes) and hands it to the other ranks by whatever means the job has.  NCCL is opened with
+ * dlopen("libnccl.so.2") on first use.  Collective: every rank calls olm_cuda_gather_records(). */
+typedef struct olm_cuda_comm olm_cuda_comm_t;
+int olm_cuda_comm_unique_id(void *id, size_t id_bytes);
+olm_cuda_comm_t *olm_cuda_comm_create(const omega_list_matcher_t *matcher, const void *id, int rank,
+                                      int world);
+int olm_cuda_comm_destroy(olm_cuda_comm_t *comm);
+/* `out` is filled on the root only (device records, valid until the root's next gather). */
+int olm_cuda_gather_records(olm_cuda_comm_t *comm, const void *dev_records, uint64_t count, int root,
+                            int no_overlap, olm_cuda_results_t *out);
+
 /* The greedy no-overlap filter (matcher.c:570-584) over `count` sorted device records, in
- * place; returns the kept count or -1. */
+ * place; returns the kept count or -1.  The records may have been produced on any stream: the
+ * call first waits for all work queued on the device (like olm_cuda_match_device). */
 int64_t olm_cuda_no_overlap(const omega_list_matcher_t *matcher, void *dev_records, uint64_t count);
 
 /* Sort device records by (offset ascending, length descending) -- the order of

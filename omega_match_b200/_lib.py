@@ -48,6 +48,10 @@ class CudaTimingC(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class ShardC(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("own_begin", "own_end", "slice_begin", "slice_end")]
+
+
 class StoreInfoC(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("flags", "smallest", "largest", "stored_patterns", "table_size",
                                          "occupied_buckets", "len1", "len2", "len3", "len4")] + [
@@ -99,6 +103,14 @@ ABI = [
      + [_ci] * 6 + [C.POINTER(CudaResultsC)]),
     ("olm_cuda_match_shard_host", _ci, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _vp]
      + [_ci] * 6 + [C.POINTER(CudaResultsC)]),
+    ("olm_cuda_matcher_create_multi", _vp, [_cp, C.POINTER(_ci), _ci]),
+    ("olm_cuda_matcher_device_count", _ci, [_vp]),
+    ("olm_shard_plan", _ci, [C.c_uint32, _ci, C.c_uint64, _ci, _ci, C.POINTER(ShardC)]),
+    ("olm_cuda_shard_plan", _ci, [_vp, C.c_uint64, _ci, _ci, C.POINTER(ShardC)]),
+    ("olm_cuda_comm_unique_id", _ci, [_vp, C.c_size_t]),
+    ("olm_cuda_comm_create", _vp, [_vp, _vp, _ci, _ci]),
+    ("olm_cuda_comm_destroy", _ci, [_vp]),
+    ("olm_cuda_gather_records", _ci, [_vp, _vp, C.c_uint64, _ci, _ci, C.POINTER(CudaResultsC)]),
     ("olm_cuda_no_overlap", C.c_int64, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_sort_records", _ci, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_last_timing", _ci, [_vp, C.POINTER(CudaTimingC)]),

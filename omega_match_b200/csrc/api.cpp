@@ -12,14 +12,20 @@
 #include "../../include/olm_b200.h"
 #include "engine.h"
 #include "host_util.h"
+#include "multi.h"
 #include "store.h"
 
 #ifndef OLM_B200_VERSION
 #define OLM_B200_VERSION "0.1.0"
 #endif
 
+struct olm_cuda_comm {
+  olm::Comm *comm = nullptr;
+};
+
 struct omega_list_matcher_struct {
-  olm::Engine *engine = nullptr;
+  olm::Engine *engine = nullptr;          // the (first) GPU's engine
+  olm::MultiMatcher *multi = nullptr;     // several GPUs in this process (owns `engine` then)
   uint8_t *file = nullptr; // mapped store
   size_t file_size = 0;
   char *temp_path = nullptr; // set when the store was compiled on the fly (matcher.c:458-481)
@@ -70,8 +76,26 @@ extern "C" {
 
 const char *omega_match_version(void) { return OLM_B200_VERSION; }
 
+namespace {
+// devices == nullptr: the default device, or the GPUs listed in OLM_CUDA_DEVICES
+omega_list_matcher_t *create_on(const char *path, int case_insensitive, int ignore_punctuation, int elide_whitespace,
+                                omega_match_pattern_store_stats_t *stats, const std::vector<int> *devices);
+} // namespace
+
 omega_list_matcher_t *omega_list_matcher_create(const char *path, int case_insensitive, int ignore_punctuation,
                                                 int elide_whitespace, omega_match_pattern_store_stats_t *stats) {
+  return create_on(path, case_insensitive, ignore_punctuation, elide_whitespace, stats, nullptr);
+}
+
+omega_list_matcher_t *olm_cuda_matcher_create_multi(const char *path, const int *devices, int n_devices) {
+  if (!path || !devices || n_devices < 1) return nullptr;
+  std::vector<int> d(devices, devices + n_devices);
+  return create_on(path, 0, 0, 0, nullptr, &d);
+}
+
+namespace {
+omega_list_matcher_t *create_on(const char *path, int case_insensitive, int ignore_punctuation, int elide_whitespace,
+                                omega_match_pattern_store_stats_t *stats, const std::vector<int> *devices) {
   if (!path) return nullptr;
   std::string load = path;
   char *temp_path = nullptr;
@@ -95,8 +119,20 @@ omega_list_matcher_t *omega_list_matcher_create(const char *path, int case_insen
   m->temp_path = temp_path;
   m->file = olm::map_whole_file(load.c_str(), &m->file_size, false);
   std::string err = "cannot map file";
+  std::vector<int> devs;
+  if (devices) {
+    devs = *devices;
+  } else if (const char *spec = std::getenv("OLM_CUDA_DEVICES")) {
+    devs = olm::parse_device_list(spec, olm_cuda_device_count());
+    if (devs.empty() && *spec) err = "OLM_CUDA_DEVICES names no usable GPU";
+  }
   try { // no exception crosses the C ABI: a store that asks for absurd allocations is a bad file
-    if (m->file) m->engine = olm::Engine::create(m->file, m->file_size, default_device(), &err);
+    if (m->file && devs.size() > 1) {
+      m->multi = olm::MultiMatcher::create(m->file, m->file_size, devs, &err);
+      if (m->multi) m->engine = m->multi->first();
+    } else if (m->file && !(devices == nullptr && std::getenv("OLM_CUDA_DEVICES") && *std::getenv("OLM_CUDA_DEVICES") && devs.empty())) {
+      m->engine = olm::Engine::create(m->file, m->file_size, devs.size() == 1 ? devs[0] : default_device(), &err);
+    }
   } catch (const std::exception &ex) {
     m->engine = nullptr;
     err = std::string("malformed store (") + ex.what() + ")";
@@ -110,6 +146,7 @@ omega_list_matcher_t *omega_list_matcher_create(const char *path, int case_insen
   omega_matcher_set_chunk_size(m, 0);
   return m;
 }
+} // namespace
 
 omega_list_matcher_t *omega_list_matcher_create_from_buffer(const char *compiled_file, const uint8_t *patterns_buffer,
                                                             uint64_t patterns_buffer_size, int case_insensitive,
@@ -127,13 +164,15 @@ int omega_list_matcher_add_stats(omega_list_matcher_t *m, omega_match_stats_t *s
   m->stats = stats;
   const char *ex = std::getenv("OLM_EXACT_STATS");
   if (ex && ex[0] == '1') m->exact_stats = true;
-  m->engine->set_exact_stats(m->exact_stats);
+  if (m->multi) m->multi->set_exact_stats(m->exact_stats);
+  else m->engine->set_exact_stats(m->exact_stats);
   return 0;
 }
 
 int omega_list_matcher_destroy(omega_list_matcher_t *m) {
   if (!m) return -1;
-  delete m->engine;
+  if (m->multi) delete m->multi; // (owns the engines)
+  else delete m->engine;
   if (m->file) olm::unmap(m->file, m->file_size);
   if (m->temp_path) {
     unlink(m->temp_path);
@@ -163,9 +202,13 @@ omega_match_results_t *omega_list_matcher_match(const omega_list_matcher_t *m, c
                                                 int word_boundary, int word_prefix, int word_suffix, int line_start,
                                                 int line_end) {
   if (!m || !m->engine) return nullptr;
-  omega_match_results_t *r = m->engine->match_host(
-      haystack, haystack_size,
-      to_flags(no_overlap, longest_only, word_boundary, word_prefix, word_suffix, line_start, line_end));
+  const olm::MatchFlags f = to_flags(no_overlap, longest_only, word_boundary, word_prefix, word_suffix, line_start, line_end);
+  if (m->multi) { // byte-range shards over the matcher's GPUs (multi.cpp)
+    omega_match_results_t *r = m->multi->match_host(haystack, haystack_size, f);
+    if (r && m->stats) m->multi->collect_stats(m->stats);
+    return r;
+  }
+  omega_match_results_t *r = m->engine->match_host(haystack, haystack_size, f);
   if (r && m->stats) m->engine->collect_stats(m->stats);
   return r;
 }
@@ -277,14 +320,57 @@ int olm_cuda_sort_records(const omega_list_matcher_t *m, void *dev_records, uint
 int olm_cuda_set_exact_stats(omega_list_matcher_t *m, int on) {
   if (!m || !m->engine) return -1;
   m->exact_stats = on != 0;
-  m->engine->set_exact_stats(m->exact_stats && m->stats); // the kernel runs only for an attached struct
+  if (m->multi) m->multi->set_exact_stats(m->exact_stats && m->stats);
+  else m->engine->set_exact_stats(m->exact_stats && m->stats); // the kernel runs only for an attached struct
   return 0;
 }
 
 int olm_cuda_last_timing(const omega_list_matcher_t *m, olm_cuda_timing_t *out) {
   if (!m || !m->engine || !out) return -1;
-  *out = m->engine->timing();
+  *out = m->multi ? m->multi->timing() : m->engine->timing();
   return 0;
+}
+
+int olm_cuda_matcher_device_count(const omega_list_matcher_t *m) { return !m || !m->engine ? -1 : (m->multi ? m->multi->size() : 1); }
+
+int olm_shard_plan(uint32_t largest_pattern, int windowed, uint64_t global_size, int world, int rank, olm_shard_t *out) {
+  if (!out || world < 1 || rank < 0 || rank >= world) return -1;
+  const olm::Shard s = olm::plan_shards(global_size, world, largest_pattern, windowed != 0)[size_t(rank)];
+  out->own_begin = s.own_begin;
+  out->own_end = s.own_end;
+  out->slice_begin = s.slice_begin;
+  out->slice_end = s.slice_end;
+  return 0;
+}
+
+int olm_cuda_shard_plan(const omega_list_matcher_t *m, uint64_t global_size, int world, int rank, olm_shard_t *out) {
+  if (!m || !m->engine) return -1;
+  const olm::Header &h = m->engine->header();
+  return olm_shard_plan(h.largest, (h.flags & olm::kFlagAnyTransform) != 0, global_size, world, rank, out);
+}
+
+int olm_cuda_comm_unique_id(void *id, size_t id_bytes) { return olm::comm_unique_id(id, id_bytes); }
+
+olm_cuda_comm_t *olm_cuda_comm_create(const omega_list_matcher_t *m, const void *id, int rank, int world) {
+  if (!m || !m->engine || m->multi) return nullptr;
+  olm::Comm *c = olm::comm_create(m->engine, id, rank, world);
+  if (!c) return nullptr;
+  auto *h = new olm_cuda_comm();
+  h->comm = c;
+  return h;
+}
+
+int olm_cuda_comm_destroy(olm_cuda_comm_t *c) {
+  if (!c) return -1;
+  olm::comm_destroy(c->comm);
+  delete c;
+  return 0;
+}
+
+int olm_cuda_gather_records(olm_cuda_comm_t *c, const void *dev_records, uint64_t count, int root, int no_overlap,
+                            olm_cuda_results_t *out) {
+  if (!c || !c->comm) return -1;
+  return olm::comm_gather(c->comm, dev_records, count, root, no_overlap != 0, out);
 }
 
 int olm_store_inspect(const char *compiled_file, olm_store_info_t *out) {

@@ -5,10 +5,11 @@
 //       path runs one group per 256 MiB segment while later segments are still being copied)
 //       -> (no_overlap filter)
 //   transform flag (matcher.c:945-1018): for every batch of <= kBatchWindows source windows
-//       transform (count / resolve / write: normalised bytes, offset map, window descriptors)
-//       -> window tails -> scan -> prefix -> place -> redo over the normalised windows; the
-//       running match total carries over from batch to batch, so the records of all windows
-//       come out in one ordered array -> (no_overlap filter)
+//       (window descriptors, only where a launch needs them: transform.cu) -> scan -> prefix ->
+//       place -> redo over the SOURCE bytes of the windows -- the scan normalises chunk by chunk
+//       in shared memory and reports source coordinates; the running match total carries over
+//       from batch to batch, so the records of all windows come out in one ordered array
+//       -> (no_overlap filter)
 //
 // place_kernel / redo_kernel write final records; the only host synchronisation of a call is the
 // read-back of the record count (needed to size the D2H copy / to detect a too small result or
@@ -32,9 +33,7 @@ namespace olm {
 
 namespace {
 
-constexpr uint32_t kBatchWindows = 64;                 // 256 MiB of source per transform batch
-constexpr uint64_t kWinStride = kWindowBytes + 256;    // normalised windows are this far apart
-constexpr uint64_t kNormFront = 256;                   // readable bytes in front of window 0
+constexpr uint32_t kBatchWindows = 64;                 // stores with a transform flag: 256 MiB of source per launch group
 constexpr uint32_t kTilesPerWindow = kWindowBytes / kTileBytes;
 constexpr uint32_t kMaxBatches = 1u << 16;
 constexpr uint64_t kSegmentBytes = uint64_t(kBatchWindows) * kWindowBytes; // host path: H2D/scan pipeline unit (256 MiB)
@@ -97,7 +96,7 @@ struct EngineImpl {
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, misc, norm, map, windows, ghost, fscratch;
+  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, tfvisible, misc, windows, ghost, fscratch, gather;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -152,7 +151,8 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   StagedStore staged;
   FilterBudget budget;
   const bool has_p23 = view.n1 || view.n2 || view.n3;
-  budget.g4_max_log2 = has_p23 ? 19 : OLM_G4_MAX_LOG2;
+  // (stores with a transform flag scan in private chunk buffers: less room for the filter)
+  budget.g4_max_log2 = (has_p23 || (view.hdr.flags & kFlagAnyTransform)) ? 19 : OLM_G4_MAX_LOG2;
   budget.p23_max_log2 = 18;
   e = stage_store(view, budget, &staged);
   if (e.empty() && check_staged_store(view, staged) != 0) e = "internal error: staged store failed its self check";
@@ -194,7 +194,11 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && cudaStreamCreateWithFlags(&impl->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
   ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
-  impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit);
+  {
+    // plain stores: scan chunks in private buffers (the ring is handed back before the scan) unless OLM_PRIV=0
+    const char *pv = std::getenv("OLM_PRIV");
+    impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit, !(pv && pv[0] == '0'));
+  }
   if (!ok || impl->geo.stages == 0) {
     delete eng;
     return fail("CUDA setup failed while uploading the store");
@@ -213,8 +217,8 @@ Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
-                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->misc,
-                    &impl_->norm, &impl_->map, &impl_->windows, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->tfvisible, &impl_->misc,
+                    &impl_->windows, &impl_->gather, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
                     &impl_->d_slens})
     b->release();
   for (auto &ev : impl_->ev)
@@ -298,12 +302,15 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   E.stats_valid = false;
 
   const bool identity_map = windowed && !(E.hdr.flags & (kFlagIgnorePunct | kFlagElideSpace));
-  if (windowed) {
+  // window descriptors: case-folding-only stores need the trimmed window lengths, stores with
+  // 2..4 byte patterns the stale-tail bytes (transform.cu)
+  const bool need_tails = windowed && E.has_short_234;
+  const bool need_desc = windowed && (identity_map || need_tails);
+  if (need_desc) {
     const uint64_t bw = std::min<uint64_t>(n_windows, kBatchWindows);
-    if (E.norm.ensure(kNormFront + bw * kWinStride + 256)) return -1;
-    if (!identity_map && E.map.ensure(bw * uint64_t(kWindowBytes) * 4)) return -1;
     if (E.windows.ensure(n_windows * sizeof(WindowDesc))) return -1;
     if (!identity_map && E.tfblocks.ensure(bw * kTfBlocksPerWindow * sizeof(TfBlock))) return -1;
+    if (!identity_map && E.tfvisible.ensure(bw * sizeof(uint2))) return -1;
   }
 
   uint64_t cap = std::max<uint64_t>(E.out_hint, n_own / 64 + 4096);
@@ -335,6 +342,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     OLM_CUDA(cudaMemsetAsync(d_redo_flags, 0, n_batches * 4, E.stream));
     OLM_CUDA(cudaMemsetAsync(d_total, 0, 128, E.stream));
     uint32_t launches = 0, scan_launches = 0;
+    uint64_t tf_batches = 0;
     OLM_CUDA(cudaEventRecord(E.ev[0], E.stream));
 
     ScanParams P{};
@@ -352,6 +360,8 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.flags = fl;
     P.stages = E.geo.stages;
     P.chunk_cap = E.geo.chunk_cap;
+    P.priv = E.geo.priv;
+    P.store_flags = E.hdr.flags;
     P.tail_byte = 0;
 
     if (!windowed) {
@@ -374,8 +384,6 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         ++scan_launches;
       }
     } else {
-      float tf_ms = 0.f;
-      (void)tf_ms;
       for (uint64_t b = 0; b < n_batches; ++b) {
         const uint64_t w0 = b * kBatchWindows;
         const uint32_t nw = (uint32_t)std::min<uint64_t>(kBatchWindows, n_windows - w0);
@@ -383,27 +391,28 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
           const uint64_t src_end = std::min<uint64_t>(n_own, (w0 + nw) * uint64_t(kWindowBytes));
           OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[seg_event_for(E, (r.own_begin - r.slice_begin) + src_end)], 0));
         }
-        TransformParams T{};
-        T.src = static_cast<const uint8_t *>(r.dev);
-        T.src_off = (r.own_begin - r.slice_begin) + w0 * kWindowBytes;
-        T.src_len = std::min<uint64_t>(uint64_t(nw) * kWindowBytes, n_own - w0 * kWindowBytes);
-        T.norm = static_cast<uint8_t *>(E.norm.p);
-        T.norm_off = kNormFront;
-        T.win_stride = kWinStride;
-        T.map = identity_map ? nullptr : static_cast<uint32_t *>(E.map.p);
-        T.windows = static_cast<WindowDesc *>(E.windows.p) + w0;
-        T.blocks = static_cast<TfBlock *>(E.tfblocks.p);
-        T.ghost = static_cast<uint8_t *>(E.ghost.p);
-        T.flags = E.hdr.flags;
-        OLM_CUDA(transform_launch(T, nw, E.has_short_234, E.sms, E.stream, &launches));
-
-        P.buf = static_cast<const uint8_t *>(E.norm.p);
-        P.buf_len = E.norm.cap & ~size_t(15);
-        P.windows = T.windows;
-        P.map = T.map;
-        P.win_stride = kWinStride;
-        P.win_buf_off = kNormFront;
+        P.buf = static_cast<const uint8_t *>(r.dev);
+        P.buf_len = (r.slice_len + 15) & ~uint64_t(15);
+        P.win_buf_off = (r.own_begin - r.slice_begin) + w0 * kWindowBytes;
         P.win_src_base = r.own_begin + w0 * kWindowBytes;
+        P.win_src_len = std::min<uint64_t>(uint64_t(nw) * kWindowBytes, n_own - w0 * kWindowBytes);
+        P.windows = nullptr;
+        if (need_desc) {
+          TransformParams T{};
+          T.src = P.buf;
+          T.src_off = P.win_buf_off;
+          T.src_len = P.win_src_len;
+          T.windows = static_cast<WindowDesc *>(E.windows.p) + w0;
+          T.blocks = static_cast<TfBlock *>(E.tfblocks.p);
+          T.visible = static_cast<uint2 *>(E.tfvisible.p);
+          T.ghost = static_cast<uint8_t *>(E.ghost.p);
+          T.flags = E.hdr.flags;
+          OLM_CUDA(cudaEventRecord(E.ev[2], E.stream));
+          OLM_CUDA(window_descs_launch(T, nw, need_tails, E.sms, E.stream, &launches));
+          OLM_CUDA(cudaEventRecord(E.ev[3], E.stream));
+          P.windows = T.windows;
+          tf_batches = b + 1;
+        }
         P.tiles_per_win = kTilesPerWindow;
         P.num_tiles = nw * kTilesPerWindow;
         P.ticket = d_tickets + b;
@@ -422,6 +431,12 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     OLM_CUDA(cudaStreamSynchronize(E.stream));
     E.last.kernel_launches = launches;
     E.last.scan_launches = scan_launches;
+    E.last.transform_ms = 0.f;
+    if (tf_batches) { // (the last batch's descriptor kernels; all batches of a call are alike)
+      float t = 0.f;
+      cudaEventElapsedTime(&t, E.ev[2], E.ev[3]);
+      E.last.transform_ms = t * float(tf_batches);
+    }
     if (total <= cap && temp_used <= temp_cap) break;
     if (temp_used > temp_cap) temp_extra += temp_used - temp_cap + temp_used / 8;
     if (attempt == 3) {
@@ -670,6 +685,27 @@ int Engine::sort_records(void *dev_records, uint64_t count) {
   OLM_CUDA(sort_records_launch(static_cast<Record *>(dev_records), static_cast<Record *>(E.out2.p), count,
                                E.fscratch.p, E.stream, &launches));
   OLM_CUDA(cudaStreamSynchronize(E.stream));
+  return 0;
+}
+
+void *Engine::stream() const { return impl_->stream; }
+
+void *Engine::gather_buffer(size_t bytes) {
+  if (cudaSetDevice(impl_->device) != cudaSuccess) return nullptr;
+  if (impl_->gather.ensure(bytes ? bytes : 16)) return nullptr;
+  return impl_->gather.p;
+}
+
+int Engine::records_to_host(void *host_dst, const void *dev_records, uint64_t count) {
+  EngineImpl &E = *impl_;
+  OLM_CUDA(cudaSetDevice(E.device));
+  if (count) OLM_CUDA(cudaMemcpyAsync(host_dst, dev_records, count * sizeof(Record), cudaMemcpyDeviceToHost, E.stream));
+  return 0;
+}
+
+int Engine::sync() {
+  OLM_CUDA(cudaSetDevice(impl_->device));
+  OLM_CUDA(cudaStreamSynchronize(impl_->stream));
   return 0;
 }
 

@@ -52,6 +52,12 @@ public:
   int64_t no_overlap_inplace(void *dev_records, uint64_t count);
   int sort_records(void *dev_records, uint64_t count);
 
+  // for the multi-GPU layer (multi.cpp)
+  void *stream() const;                      // the matcher's cudaStream_t
+  void *gather_buffer(size_t bytes);         // device memory for gathered records (kept until the next request)
+  int records_to_host(void *host_dst, const void *dev_records, uint64_t count); // asynchronous, on stream()
+  int sync();                                // waits for stream()
+
   const olm_cuda_timing_t &timing() const;
   void collect_stats(omega_match_stats_t *accum); // adds the counters of the last call
   // While on, every call also runs stats_kernel (stats.cuh) so that collect_stats() reports the

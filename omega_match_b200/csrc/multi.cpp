@@ -1,0 +1,403 @@
+// multi.cpp -- several GPUs behind the C ABI: byte-range shards, ownership rule, one
+// gather.  Two ways to use more than one GPU, both without anything but C/C++, CUDA and NCCL:
+//
+//  (1) ONE PROCESS, N GPUS -- `MultiMatcher`.  A matcher created while OLM_CUDA_DEVICES lists
+//      several GPUs (or through olm_cuda_matcher_create_multi) owns one engine per GPU.
+//      omega_list_matcher_match(host haystack) then is: N host threads, each driving its GPU's
+//      engine over its byte range (its own PCIe link: segmented H2D overlapped with the scan),
+//      the per-GPU totals give every shard its place in the one result array, and the records are
+//      copied out by all GPUs at once, each into its range of that (pinned) array.  `no_overlap`
+//      -- the one filter that crosses shards -- first gathers the records on the first GPU over
+//      NVLink (peer copies, final order = shard order) and runs once there.
+//
+//  (2) ONE PROCESS PER GPU -- `olm_cuda_comm_t`.  Every rank scans its shard
+//      (olm_cuda_match_shard[_host]); olm_cuda_gather_records() exchanges the counts
+//      (ncclAllGather of 8 bytes) and moves the records to the root's HBM with one group of
+//      ncclSend / ncclRecv on the matcher's stream (NVLink / NVSwitch), then applies `no_overlap`
+//      there.  NCCL is opened with dlopen() the first time a communicator is made, so the library
+//      has no link-time dependency on it and single-GPU users never load it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "multi.h"
+#include "scan.cuh"
+
+namespace olm {
+
+namespace {
+
+#define OLM_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      std::fprintf(stderr, "libomega_match(b200): %s failed: %s (%s:%d)\n", #expr,              \
+                   cudaGetErrorString(_e), __FILE__, __LINE__);                                 \
+      return -1;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+// ---- NCCL, loaded on demand ------------------------------------------------------------------
+struct Nccl {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+Nccl &nccl() {
+  static Nccl n = [] {
+    Nccl x;
+    // a copy that is already in the process (e.g. the one a host framework brought along) wins
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      x.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (x.lib) break;
+    }
+    if (!x.lib) {
+      std::fprintf(stderr, "libomega_match(b200): cannot load NCCL (%s)\n", dlerror());
+      return x;
+    }
+    auto sym = [&](const char *s) { return dlsym(x.lib, s); };
+    x.GetUniqueId = reinterpret_cast<decltype(x.GetUniqueId)>(sym("ncclGetUniqueId"));
+    x.CommInitRank = reinterpret_cast<decltype(x.CommInitRank)>(sym("ncclCommInitRank"));
+    x.CommDestroy = reinterpret_cast<decltype(x.CommDestroy)>(sym("ncclCommDestroy"));
+    x.AllGather = reinterpret_cast<decltype(x.AllGather)>(sym("ncclAllGather"));
+    x.Send = reinterpret_cast<decltype(x.Send)>(sym("ncclSend"));
+    x.Recv = reinterpret_cast<decltype(x.Recv)>(sym("ncclRecv"));
+    x.GroupStart = reinterpret_cast<decltype(x.GroupStart)>(sym("ncclGroupStart"));
+    x.GroupEnd = reinterpret_cast<decltype(x.GroupEnd)>(sym("ncclGroupEnd"));
+    x.GetErrorString = reinterpret_cast<decltype(x.GetErrorString)>(sym("ncclGetErrorString"));
+    x.ok = x.GetUniqueId && x.CommInitRank && x.CommDestroy && x.AllGather && x.Send && x.Recv && x.GroupStart &&
+           x.GroupEnd && x.GetErrorString;
+    if (!x.ok) std::fprintf(stderr, "libomega_match(b200): the NCCL library lacks a symbol this library needs\n");
+    return x;
+  }();
+  return n;
+}
+
+#define OLM_NCCL(expr)                                                                          \
+  do {                                                                                          \
+    ncclResult_t _r = (expr);                                                                   \
+    if (_r != ncclSuccess) {                                                                    \
+      std::fprintf(stderr, "libomega_match(b200): %s failed: %s (%s:%d)\n", #expr,              \
+                   nccl().GetErrorString(_r), __FILE__, __LINE__);                              \
+      return -1;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+} // namespace
+
+// ================================ (1) one process, N GPUs =========================================
+
+std::vector<int> parse_device_list(const char *spec, int n_devices) {
+  std::vector<int> out;
+  if (!spec || !*spec) return out;
+  std::string s(spec);
+  if (s == "all") {
+    for (int i = 0; i < n_devices; ++i) out.push_back(i);
+    return out;
+  }
+  size_t at = 0;
+  while (at < s.size()) {
+    size_t end = s.find(',', at);
+    if (end == std::string::npos) end = s.size();
+    const std::string tok = s.substr(at, end - at);
+    const size_t dash = tok.find('-');
+    char *e1 = nullptr;
+    if (dash == std::string::npos) {
+      const long v = std::strtol(tok.c_str(), &e1, 10);
+      if (tok.empty() || *e1 || v < 0 || v >= n_devices) return {};
+      out.push_back((int)v);
+    } else {
+      const std::string a = tok.substr(0, dash), b = tok.substr(dash + 1);
+      char *e2 = nullptr;
+      const long lo = std::strtol(a.c_str(), &e1, 10), hi = std::strtol(b.c_str(), &e2, 10);
+      if (a.empty() || b.empty() || *e1 || *e2 || lo < 0 || hi < lo || hi >= n_devices) return {};
+      for (long v = lo; v <= hi; ++v) out.push_back((int)v);
+    }
+    at = end + 1;
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+  return out;
+}
+
+std::vector<Shard> plan_shards(uint64_t size, int world, uint32_t largest_pattern, bool windowed) {
+  std::vector<Shard> shards;
+  const uint64_t unit = windowed ? kWindowBytes : 4096;
+  const uint64_t units = (size + unit - 1) / unit;
+  for (int r = 0; r < world; ++r) {
+    Shard s;
+    s.own_begin = std::min<uint64_t>(size, units * (uint64_t)r / (uint64_t)world * unit);
+    s.own_end = r + 1 < world ? std::min<uint64_t>(size, units * (uint64_t)(r + 1) / (uint64_t)world * unit) : size;
+    if (windowed) { // windows are independent: no halo at all
+      s.slice_begin = s.own_begin;
+      s.slice_end = s.own_end;
+    } else { // 16 bytes in front (alignment + the previous byte), the longest pattern + 1 behind
+      s.slice_begin = s.own_begin >= 16 ? s.own_begin - 16 : 0;
+      s.slice_end = std::min<uint64_t>(size, s.own_end + largest_pattern + 1);
+    }
+    shards.push_back(s);
+  }
+  return shards;
+}
+
+MultiMatcher *MultiMatcher::create(const uint8_t *file, size_t size, const std::vector<int> &devices, std::string *err) {
+  auto *m = new MultiMatcher();
+  for (int d : devices) {
+    Engine *e = Engine::create(file, size, d, err);
+    if (!e) {
+      delete m;
+      return nullptr;
+    }
+    m->engines_.push_back(e);
+  }
+  // peer access towards the first GPU: the no_overlap gather copies over NVLink
+  for (size_t g = 1; g < m->engines_.size(); ++g) {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, m->engines_[g]->device(), m->engines_[0]->device()) == cudaSuccess && can) {
+      cudaSetDevice(m->engines_[g]->device());
+      if (cudaDeviceEnablePeerAccess(m->engines_[0]->device(), 0) != cudaSuccess) cudaGetLastError(); // (already enabled: fine)
+      cudaSetDevice(m->engines_[0]->device());
+      if (cudaDeviceEnablePeerAccess(m->engines_[g]->device(), 0) != cudaSuccess) cudaGetLastError();
+    }
+  }
+  return m;
+}
+
+MultiMatcher::~MultiMatcher() {
+  for (Engine *e : engines_) delete e;
+}
+
+omega_match_results_t *MultiMatcher::match_host(const uint8_t *haystack, size_t n, const MatchFlags &f) {
+  const int N = (int)engines_.size();
+  auto *results = static_cast<omega_match_results_t *>(std::malloc(sizeof(omega_match_results_t)));
+  if (!results) return nullptr;
+  results->count = 0;
+  results->matches = static_cast<omega_match_result_t *>(std::malloc(sizeof(omega_match_result_t)));
+  last_ = olm_cuda_timing_t{};
+  scanned_.assign(N, false);
+  if (n == 0 || !haystack) return results;
+  auto bail = [&]() -> omega_match_results_t * {
+    if (!pinned_result_release(results->matches)) std::free(results->matches);
+    std::free(results);
+    return nullptr;
+  };
+  const Header &h = engines_[0]->header();
+  const bool windowed = h.flags & kFlagAnyTransform;
+  const std::vector<Shard> plan = plan_shards(n, N, h.largest, windowed);
+  MatchFlags fs = f;
+  fs.no_overlap = false; // crosses shards: once, on the gathered records
+  std::vector<olm_cuda_results_t> res(N);
+  std::vector<int> rc(N, 0);
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < N; ++g) {
+      res[g] = olm_cuda_results_t{0, nullptr, engines_[g]->device()};
+      const Shard &s = plan[g];
+      if (s.own_end <= s.own_begin) continue;
+      scanned_[g] = true;
+      th.emplace_back([&, g]() {
+        const Shard &sh = plan[g];
+        ScanRange r;
+        r.slice_begin = sh.slice_begin;
+        r.slice_len = sh.slice_end - sh.slice_begin;
+        r.own_begin = sh.own_begin;
+        r.own_end = sh.own_end;
+        r.global_size = n;
+        r.match_ptr_base = reinterpret_cast<uint64_t>(haystack);
+        rc[g] = engines_[g]->match_shard_host(haystack + sh.slice_begin, r, fs, &res[g]);
+      });
+    }
+    for (auto &t : th) t.join();
+  }
+  uint64_t total = 0;
+  std::vector<uint64_t> off(N, 0);
+  for (int g = 0; g < N; ++g) {
+    if (rc[g] != 0) return bail();
+    off[g] = total;
+    total += res[g].count;
+    const olm_cuda_timing_t &t = engines_[g]->timing();
+    last_.scan_ms = std::max(last_.scan_ms, t.scan_ms);
+    last_.transform_ms = std::max(last_.transform_ms, t.transform_ms);
+    last_.total_ms = std::max(last_.total_ms, t.total_ms);
+    last_.h2d_ms = std::max(last_.h2d_ms, t.h2d_ms);
+    last_.scan_launches += t.scan_launches;
+    last_.kernel_launches += t.kernel_launches;
+    last_.matches_before_filter += t.matches_before_filter;
+  }
+  if (total == 0) return results;
+
+  Engine *E0 = engines_[0];
+  const void *src0 = nullptr; // records that leave through the first GPU (no_overlap)
+  uint64_t kept = total;
+  if (f.no_overlap && total > 1) {
+    void *buf = E0->gather_buffer(total * sizeof(Record));
+    if (!buf) return bail();
+    cudaStream_t s0 = static_cast<cudaStream_t>(E0->stream());
+    for (int g = 0; g < N; ++g)
+      if (res[g].count &&
+          cudaMemcpyPeerAsync(static_cast<uint8_t *>(buf) + off[g] * sizeof(Record), E0->device(), res[g].records,
+                              engines_[g]->device(), res[g].count * sizeof(Record), s0) != cudaSuccess)
+        return bail();
+    if (cudaStreamSynchronize(s0) != cudaSuccess) return bail();
+    const int64_t k = E0->no_overlap_inplace(buf, total);
+    if (k < 0) return bail();
+    kept = (uint64_t)k;
+    last_.filter_ms = E0->timing().filter_ms;
+    src0 = buf;
+  }
+  std::free(results->matches);
+  const size_t rbytes = std::max<uint64_t>(kept, 1) * sizeof(omega_match_result_t);
+  results->matches = nullptr;
+  if (rbytes >= kPinnedResultMin) results->matches = static_cast<omega_match_result_t *>(pinned_result_alloc(rbytes));
+  if (!results->matches) results->matches = static_cast<omega_match_result_t *>(std::malloc(rbytes));
+  if (!results->matches) {
+    std::free(results);
+    return nullptr;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaSetDevice(E0->device());
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, static_cast<cudaStream_t>(E0->stream()));
+  bool ok = true;
+  if (src0) {
+    ok = E0->records_to_host(results->matches, src0, kept) == 0;
+  } else { // every GPU copies its records into its range of the one array, all links at once
+    for (int g = 0; g < N && ok; ++g)
+      if (res[g].count) ok = engines_[g]->records_to_host(results->matches + off[g], res[g].records, res[g].count) == 0;
+  }
+  for (int g = 0; g < N; ++g)
+    if (engines_[g]->sync() != 0) ok = false;
+  cudaSetDevice(E0->device());
+  cudaEventRecord(e1, static_cast<cudaStream_t>(E0->stream()));
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&last_.d2h_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!ok) return bail();
+  results->count = kept;
+  return results;
+}
+
+void MultiMatcher::collect_stats(omega_match_stats_t *s) {
+  for (size_t g = 0; g < engines_.size(); ++g)
+    if (g < scanned_.size() && scanned_[g]) engines_[g]->collect_stats(s);
+}
+void MultiMatcher::set_exact_stats(bool on) {
+  for (Engine *e : engines_) e->set_exact_stats(on);
+}
+
+// ================================ (2) one process per GPU =========================================
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  Engine *engine = nullptr;
+  unsigned long long *d_counts = nullptr; // world entries
+  std::vector<unsigned long long> h_counts;
+};
+
+Comm *comm_create(Engine *engine, const void *id, int rank, int world) {
+  if (!engine || !id || world < 1 || rank < 0 || rank >= world || !nccl().ok) return nullptr;
+  if (cudaSetDevice(engine->device()) != cudaSuccess) return nullptr;
+  auto *c = new Comm();
+  c->rank = rank;
+  c->world = world;
+  c->engine = engine;
+  c->h_counts.assign(world, 0);
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof uid);
+  if (cudaMalloc(&c->d_counts, sizeof(unsigned long long) * world) != cudaSuccess ||
+      nccl().CommInitRank(&c->comm, world, uid, rank) != ncclSuccess) {
+    std::fprintf(stderr, "libomega_match(b200): cannot create the NCCL communicator (rank %d of %d)\n", rank, world);
+    if (c->d_counts) cudaFree(c->d_counts);
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void comm_destroy(Comm *c) {
+  if (!c) return;
+  cudaSetDevice(c->engine->device());
+  if (c->comm) nccl().CommDestroy(c->comm);
+  if (c->d_counts) cudaFree(c->d_counts);
+  delete c;
+}
+
+int comm_unique_id(void *id, size_t bytes) {
+  if (!id || bytes < sizeof(ncclUniqueId) || !nccl().ok) return -1;
+  ncclUniqueId uid;
+  OLM_NCCL(nccl().GetUniqueId(&uid));
+  std::memcpy(id, &uid, sizeof uid);
+  return 0;
+}
+
+int comm_gather(Comm *c, const void *dev_records, uint64_t count, int root, bool no_overlap, olm_cuda_results_t *out) {
+  if (!c || !out || root < 0 || root >= c->world) return -1;
+  Engine *E = c->engine;
+  OLM_CUDA(cudaSetDevice(E->device()));
+  cudaStream_t st = static_cast<cudaStream_t>(E->stream());
+  out->count = 0;
+  out->records = nullptr;
+  out->device = E->device();
+  // counts of all ranks (in place: every rank contributes its own entry)
+  const unsigned long long mine = count;
+  OLM_CUDA(cudaMemcpyAsync(c->d_counts + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+  OLM_NCCL(nccl().AllGather(c->d_counts + c->rank, c->d_counts, 1, ncclUint64, c->comm, st));
+  OLM_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->d_counts, sizeof(unsigned long long) * c->world, cudaMemcpyDeviceToHost, st));
+  OLM_CUDA(cudaStreamSynchronize(st));
+  uint64_t total = 0;
+  std::vector<uint64_t> off(c->world, 0);
+  for (int r = 0; r < c->world; ++r) {
+    off[r] = total;
+    total += c->h_counts[r];
+  }
+  if (c->rank != root) { // shards are ordered: the root lays the ranks' records out in rank order
+    if (count) OLM_NCCL(nccl().Send(dev_records, count * sizeof(Record), ncclUint8, root, c->comm, st));
+    OLM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  uint8_t *buf = nullptr;
+  if (total) {
+    buf = static_cast<uint8_t *>(E->gather_buffer(total * sizeof(Record)));
+    if (!buf) return -1;
+    if (count)
+      OLM_CUDA(cudaMemcpyAsync(buf + off[root] * sizeof(Record), dev_records, count * sizeof(Record), cudaMemcpyDeviceToDevice, st));
+    OLM_NCCL(nccl().GroupStart());
+    for (int r = 0; r < c->world; ++r)
+      if (r != root && c->h_counts[r])
+        OLM_NCCL(nccl().Recv(buf + off[r] * sizeof(Record), c->h_counts[r] * sizeof(Record), ncclUint8, r, c->comm, st));
+    OLM_NCCL(nccl().GroupEnd());
+    OLM_CUDA(cudaStreamSynchronize(st));
+  }
+  uint64_t kept = total;
+  if (no_overlap && total > 1) {
+    const int64_t k = E->no_overlap_inplace(buf, total);
+    if (k < 0) return -1;
+    kept = (uint64_t)k;
+  }
+  out->count = kept;
+  out->records = buf;
+  return 0;
+}
+
+} // namespace olm

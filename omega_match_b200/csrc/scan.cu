@@ -48,16 +48,17 @@
 
 #include "olm_classes.h"
 #include "olm_format.h"
+#include "scan_device.cuh"
 
 namespace olm {
 
 namespace {
 
-constexpr uint32_t kFull = 0xFFFFFFFFu;
+using namespace dev;
+
 #ifndef OLM_FAST_UNROLL
 #define OLM_FAST_UNROLL 2
 #endif
-constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 // chunks a scanning warp takes per grab.  2 was slower with the 4-stage ring of an earlier version
 // (nothing left to prefetch into); kept as a build knob for the deeper rings.
 #ifndef OLM_GRAB
@@ -69,22 +70,6 @@ static_assert(kGrab >= 1 && kTileChunks % kGrab == 0, "a grab stays inside one t
 #define OLM_CLS_SKIP_BITMAP 0
 #endif
 
-struct StageInfo { // written by the producer lane, read by everyone after the mbarrier wait
-  unsigned long long p0;   // segment-relative position of the tile's first byte
-  uint32_t rem0;           // min(segment length - p0, 2^31): segment bytes from the tile's first position on
-  uint32_t nscan;          // start positions of this tile to evaluate (<= kTileBytes)
-  unsigned long long _pad2;
-  long long boff;          // buffer offset of position p0
-  unsigned long long emit_base;
-  uint32_t tile;           // launch-local tile index, kNoTile = no more work
-  uint32_t tail;
-  uint32_t win;
-  uint32_t staged;         // bytes valid behind p0 in the stage buffer
-  uint32_t seq;            // tile iteration of the CTA this entry describes (written first)
-  uint32_t stage_par;      // stage of the ring that holds the tile | parity of its mbarrier phase << 16
-};
-static_assert(sizeof(StageInfo) == 64, "StageInfo is 64 bytes");
-
 // shared memory header (kSmemHeader bytes)
 struct SmemHeader {
   uint64_t full[kMaxStages];
@@ -95,9 +80,6 @@ struct SmemHeader {
 };
 static_assert(sizeof(SmemHeader) <= kSmemHeader, "header does not fit");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -136,9 +118,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
-// Shared memory by 32-bit shared-space address.  The scanning warps never dereference a generic
-// pointer into shared memory: every generic access makes nvcc recompute the shared window base
-// (S2R SR_CgaCtaId + LEA, on the slow XU pipe) -- ~35 of them per chunk saturated that pipe.
 // One bucket of the key table.  The buckets never hit in L1 (a 32 MiB table probed at random), so
 // they are read with ld.global.cg -- cached in L2 only: 620 vs 608 GB/s at 1 M patterns with
 // __ldg; ld.global.nc.L1::no_allocate: 253.  OLM_KEY_LOAD=0 restores __ldg.
@@ -153,50 +132,6 @@ __device__ __forceinline__ uint4 ld_keys(const uint4 *p) {
   asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 #endif
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t lds16(uint32_t a) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint2 lds64(uint32_t a) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long lds64u(uint32_t a) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
-}
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts64u(uint32_t a, unsigned long long v) {
-  asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
-}
-// little-endian 32-bit word at an arbitrary shared-memory byte address
-__device__ __forceinline__ uint32_t lds_le32(uint32_t a) {
-  const uint32_t lo = lds32(a & ~3u), hi = lds32((a & ~3u) + 4);
-  return __funnelshift_r(lo, hi, a << 3);
 }
 __device__ __forceinline__ void mbar_arrive32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -216,26 +151,8 @@ __device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 
-struct TileCtx {
-  uint32_t sb32;     // stage buffer (shared-space address); byte sb32 + kTilePre + i is tile position i
-  unsigned long long p0;
-  long long boff;
-  uint32_t rem0;   // min(len - p0, 2^31): bytes of the segment from the tile's first position on
-  uint32_t nscan;  // positions of this tile to evaluate (<= kTileBytes)
-  uint32_t staged, tail;
-  bool first;      // p0 == 0
-};
-
-// One final record.  `pos` is segment relative; with a map (window mode) it is translated back
-// to source coordinates (matcher.c:986-997).
-__device__ __forceinline__ void put_record(const ScanParams &P, unsigned long long r, unsigned long long emit_base,
-                                           unsigned long long pos, uint32_t len, const uint32_t *map) {
-  unsigned long long off = emit_base + pos;
-  if (map) {
-    const uint32_t a = __ldg(map + pos), b = __ldg(map + pos + len - 1);
-    off = emit_base + a;
-    len = b - a + 1;
-  }
+// One final record (omega_match_result_t, list_matcher.h:19-23) in source coordinates.
+__device__ __forceinline__ void put_record(const ScanParams &P, unsigned long long r, unsigned long long off, uint32_t len) {
   Record *o = P.out + r;
   o->offset = off;
   *reinterpret_cast<unsigned long long *>(&o->len) = (unsigned long long)len;
@@ -244,7 +161,9 @@ __device__ __forceinline__ void put_record(const ScanParams &P, unsigned long lo
 
 enum ChunkMode { kStageMode = 0, kCountMode = 1, kDirectMode = 2 };
 
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
+// XF: the store has a transform flag (window mode): chunks are case-folded or normalised into the
+// warp's private buffer; plain stores never see that code.
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF>
 struct Scanner {
   const ScanParams &P;
   const uint32_t *g4s;
@@ -256,12 +175,31 @@ struct Scanner {
   mutable uint32_t n_hits = 0, n_miss = 0, n_cmp = 0, n_long_hits = 0;
   mutable uint32_t stat_inc = 1; // 0 while a position is evaluated a second time
 
+  uint32_t xf32 = 0; // normalising stores: the warp's rows / walk state (scan_device.cuh), else 0
+
   __device__ __forceinline__ Scanner(const ScanParams &p, const uint32_t *g4, const uint32_t *p23)
       : P(p), g4s(g4), p23s(p23), fl(p.flags) {}
 
+  // Byte `rel` of the segment T describes; kBeyond when a normalised window ends before it.
   __device__ __forceinline__ uint32_t hay_byte(const TileCtx &T, uint32_t rel) const {
     if (rel < T.staged) return lds8(T.sb32 + kTilePre + rel);
-    return P.buf[T.boff + (long long)rel];
+    if (XF && xf32) return xf_walk(P.buf + T.boff, P.store_flags, xf32, rel, false).byte;
+    const uint32_t c = P.buf[T.boff + (long long)rel];
+    return XF ? upper_byte(c) : c; // (a window-mode store without rows only folds case)
+  }
+  // A match at position tpos of len bytes, as the matcher saw it -> in source coordinates relative
+  // to T's first source byte (matcher.c:986-997: the first and the last byte are mapped back).
+  __device__ __forceinline__ uint32_t src_of(const TileCtx &T, uint32_t j) const {
+    const uint32_t tab_n = lds32(xf32 + kXfCurIdx); // bytes the per-byte table covers
+    if (j < tab_n) return xf_src(P.buf + T.boff, P.store_flags, xf32, j);
+    if (j < T.staged) return lds32(xf32 + kXfExt + 4u * (j - tab_n));
+    return xf_walk(P.buf + T.boff, P.store_flags, xf32, j, false).src;
+  }
+  __device__ __forceinline__ uint32_t locate_start(const TileCtx &T, uint32_t tpos) const {
+    return (XF && xf32) ? src_of(T, tpos) : tpos;
+  }
+  __device__ __forceinline__ uint32_t locate_len(const TileCtx &T, uint32_t tpos, uint32_t len, uint32_t spos) const {
+    return (XF && xf32) ? src_of(T, tpos + len - 1) - spos + 1 : len;
   }
 
   // bytes [8, len) of a candidate against the pattern store (bytes 0..7 are already equal)
@@ -277,6 +215,7 @@ struct Scanner {
     if (!(fl & (kWordBoundary | kWordSuffix | kLineEnd))) return true;
     if (tpos + len >= T.rem0) return true;
     const uint32_t c = hay_byte(T, tpos + len);
+    if (c == kBeyond) return true; // the normalised window ends with the match
     if ((fl & (kWordBoundary | kWordSuffix)) && is_word_byte(c)) return false;
     if ((fl & kLineEnd) && !is_line_end_byte(c)) return false;
     return true;
@@ -285,8 +224,12 @@ struct Scanner {
   // haystack[pos+L] without a bound (:812,:830,:848) -> `tail` stands in at pos+L == n.
   __device__ __forceinline__ bool end_ok_short(const TileCtx &T, uint32_t tpos, uint32_t L) const {
     if (!(fl & (kWordBoundary | kWordSuffix | kLineEnd))) return true;
-    const bool inside = tpos + L < T.rem0;
-    const uint32_t c = inside ? hay_byte(T, tpos + L) : T.tail;
+    bool inside = tpos + L < T.rem0;
+    uint32_t c = inside ? hay_byte(T, tpos + L) : T.tail;
+    if (c == kBeyond) { // the normalised window ends with the match
+      inside = false;
+      c = T.tail;
+    }
     if (fl & kWordBoundary) {
       if (L == 1) {
         if (inside && is_word_byte(c)) return false;
@@ -556,11 +499,12 @@ struct Scanner {
   //                do not fit, *overflow is set (the tile goes on the redo list);
   //   kCountMode : nothing is written;
   //   kDirectMode: matches go to P.out[out_base ...] as final records.
+  //   `cbase`: position of the chunk inside T (0 when T is a chunk in a private buffer); staged
+  //   entries and records are in SOURCE coordinates (locate()).
   template <int MODE>
   __device__ __forceinline__ uint32_t verify_batch(const TileCtx &T, uint32_t q2, uint32_t n, uint32_t lane,
-                                                   uint32_t stage, uint32_t used, uint32_t cap,
-                                                   unsigned long long out_base, unsigned long long emit_base,
-                                                   const uint32_t *map, uint32_t *overflow) const {
+                                                   uint32_t stage, uint32_t used, uint32_t cap, uint32_t cbase,
+                                                   unsigned long long out_base, uint32_t *overflow) const {
     bool mine = lane < n;
     const unsigned long long ent = mine ? lds64u(q2 + 8u * lane) : 0ull; // q2, stage: shared-space addresses
     const uint32_t slot = (uint32_t)ent, hi = (uint32_t)(ent >> 32);
@@ -601,13 +545,17 @@ struct Scanner {
         }
         at = used + pre;
       }
+      // (the start of all matches of a position is translated once)
+      const uint32_t spos = (MODE != kCountMode && cnt > skip) ? locate_start(T, tpos) : 0u;
       auto put = [&](uint32_t i, uint32_t len) {
+        if (MODE == kCountMode) return;
+        const uint32_t slen = locate_len(T, tpos, len, spos);
         if (MODE == kDirectMode) {
           const unsigned long long r = out_base + at + i;
-          if (r < P.out_cap) write_record(r, emit_base, T.p0 + tpos, len, map);
+          if (r < P.out_cap) put_record(P, r, T.gbase + spos, slen);
         } else if (MODE == kStageMode) {
-          if (at + i < cap && !(len >> kPackLenBits)) {
-            sts32(stage + 4u * (at + i), (tpos << kPackLenBits) | len);
+          if (at + i < cap && !(slen >> kPackLenBits)) {
+            sts32(stage + 4u * (at + i), ((spos - cbase) << kPackLenBits) | slen);
           } else {
             *overflow = 1;
           }
@@ -632,8 +580,7 @@ struct Scanner {
   template <int MODE>
   __device__ __forceinline__ uint32_t scan_chunk(const TileCtx &T, uint32_t cbase, uint32_t lane, uint32_t stage,
                                                  uint32_t cap, uint32_t q1, uint32_t q2,
-                                                 unsigned long long out_base, unsigned long long emit_base,
-                                                 const uint32_t *map, uint32_t *overflow) const {
+                                                 unsigned long long out_base, uint32_t *overflow) const {
     uint32_t cg, cp;
     const uint32_t lpos = cbase + lane * 16;
     stage1(T, lpos, cg, cp);
@@ -685,7 +632,7 @@ struct Scanner {
       const bool last = base + 32 * kProbeUnroll >= total;
       while (q2n >= 32 || (last && q2n)) {
         const uint32_t nb = q2n < 32 ? q2n : 32;
-        found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, out_base, emit_base, map, overflow);
+        found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, cbase, out_base, overflow);
         const uint32_t rest = q2n - nb; // <= 63
         const unsigned long long mv0 = lane < rest ? lds64u(q2 + 8u * (32 + lane)) : 0ull;
         const unsigned long long mv1 = 32 + lane < rest ? lds64u(q2 + 8u * (64 + lane)) : 0ull;
@@ -708,9 +655,7 @@ struct Scanner {
   __device__ __forceinline__ uint32_t scan_chunk_fast(const TileCtx &T, uint32_t sb_off, uint32_t g4_off,
                                                       uint32_t p23_off, uint32_t q1_off, uint32_t q2_off,
                                                       uint32_t cbase, uint32_t lane, uint32_t stage, uint32_t cap,
-                                                      unsigned long long out_base,
-                                                      unsigned long long emit_base, const uint32_t *map,
-                                                      uint32_t *overflow) const {
+                                                      unsigned long long out_base, uint32_t *overflow) const {
     const uint32_t lpos = cbase + lane * 16;
     const uint32_t src = sb_off + kTilePre + lpos;
     const uint4 v = lds128(src);
@@ -853,7 +798,7 @@ struct Scanner {
       const bool last = base + 32 * U >= total;
       while (q2n >= 32 || (last && q2n)) {
         const uint32_t nb = q2n < 32 ? q2n : 32;
-        found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, out_base, emit_base, map, overflow);
+        found += verify_batch<MODE>(T, q2, nb, lane, stage, found, cap, cbase, out_base, overflow);
         const uint32_t rest = q2n - nb; // <= 63
         const unsigned long long mv0 = lane < rest ? lds64u(q2 + 8u * (32 + lane)) : 0ull;
         const unsigned long long mv1 = 32 + lane < rest ? lds64u(q2 + 8u * (64 + lane)) : 0ull;
@@ -866,11 +811,6 @@ struct Scanner {
     }
     __syncwarp();
     return found;
-  }
-
-  __device__ __forceinline__ void write_record(unsigned long long r, unsigned long long emit_base,
-                                               unsigned long long pos, uint32_t len, const uint32_t *map) const {
-    put_record(P, r, emit_base, pos, len, map);
   }
 
   __device__ __forceinline__ void flush_stats(uint32_t lane) const {
@@ -891,42 +831,7 @@ struct Scanner {
   }
 };
 
-// Fills `I` for launch-local tile t ...
-__device__ __forceinline__ void fill_tile(const ScanParams &P, uint32_t t, StageInfo &I) {
-  I.tile = t;
-  uint32_t win = 0;
-  unsigned long long len, end;
-  if (P.flags & kWindowMode) {
-    win = t / P.tiles_per_win;
-    const WindowDesc wd = P.windows[win];
-    I.p0 = (unsigned long long)(t % P.tiles_per_win) * kTileBytes;
-    len = wd.norm_len;
-    end = wd.norm_len;
-    I.boff = (long long)(P.win_buf_off + (unsigned long long)win * P.win_stride + I.p0);
-    I.tail = wd.tail;
-    I.emit_base = P.win_src_base + (unsigned long long)win * kWindowBytes;
-  } else {
-    I.p0 = P.scan_begin + (unsigned long long)t * kTileBytes;
-    len = P.seg_len;
-    end = P.scan_end < P.seg_len ? P.scan_end : P.seg_len;
-    I.boff = P.seg_buf_off + (long long)I.p0;
-    I.tail = P.tail_byte;
-    I.emit_base = 0;
-  }
-  I.win = win;
-  I.staged = 0;
-  I.rem0 = 0;
-  I.nscan = 0;
-  if (I.p0 < end) {
-    long long e = I.boff + kTileBytes + kTileHalo;
-    if (e > (long long)P.buf_len) e = (long long)P.buf_len;
-    I.staged = (uint32_t)(e - I.boff);
-    const unsigned long long left = len - I.p0, ns = end - I.p0;
-    I.rem0 = left > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)left;
-    I.nscan = ns > (unsigned long long)kTileBytes ? (uint32_t)kTileBytes : (uint32_t)ns;
-  }
-}
-// ... and starts its bulk copy into `dst` (a stage buffer), completing on `bar`.
+// Starts the bulk copy of tile `I` into `dst` (a stage buffer), completing on `bar`.
 __device__ __forceinline__ void copy_tile(const ScanParams &P, const StageInfo &I, uint8_t *dst, uint64_t *bar) {
   if (I.nscan) {
     const long long pre = I.boff >= kTilePre ? kTilePre : 0;
@@ -937,14 +842,47 @@ __device__ __forceinline__ void copy_tile(const ScanParams &P, const StageInfo &
     mbar_expect_tx(bar, 0); // empty tile: the phase completes at once
   }
 }
-__device__ __forceinline__ void start_tile(const ScanParams &P, uint32_t t, StageInfo &I, uint8_t *dst, uint64_t *bar) {
-  fill_tile(P, t, I);
-  copy_tile(P, I, dst, bar);
+struct SmemLayout {
+  SmemHeader *H;
+  uint8_t *ring;
+  uint32_t *g4s, *p23s, *staging;
+  uint16_t *q1;
+  unsigned long long *q2;
+  uint8_t *priv, *xf; // per warp: private chunk buffer (kPrivBytes), rows of a normalised chunk (kXfRowBytes)
+};
+// header | ring | g4 | p23 | Q2 (8-byte entries) | staging | Q1 | private chunk buffers | rows
+template <bool HAS_G4, bool HAS_P23>
+__device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, size_t ring_bytes, uint32_t staging_words) {
+  SmemLayout L;
+  L.H = reinterpret_cast<SmemHeader *>(smem);
+  L.ring = smem + kSmemHeader;
+  L.g4s = reinterpret_cast<uint32_t *>(L.ring + ring_bytes);
+  L.p23s = L.g4s + (HAS_G4 ? P.st.g4_words : 0);
+  L.q2 = reinterpret_cast<unsigned long long *>(L.p23s + (HAS_P23 ? P.st.p23_words : 0));
+  L.staging = reinterpret_cast<uint32_t *>(L.q2 + kScanWarps * kQ2Entries);
+  L.q1 = reinterpret_cast<uint16_t *>(L.staging + staging_words);
+  L.priv = reinterpret_cast<uint8_t *>(L.q1) + kQ1Bytes;
+  L.xf = L.priv + (size_t)kScanWarps * kPrivBytes;
+  return L;
 }
-
+// the fields of a tile description the scanning warps need, from shared memory
+__device__ __forceinline__ void load_info(uint32_t I32, StageInfo &I) {
+  const uint2 gb = lds64(I32 + (uint32_t)offsetof(StageInfo, gbase));
+  const uint2 p0 = lds64(I32 + (uint32_t)offsetof(StageInfo, p0));
+  const uint2 bo = lds64(I32 + (uint32_t)offsetof(StageInfo, boff));
+  const uint2 rn = lds64(I32 + (uint32_t)offsetof(StageInfo, rem0));
+  I.gbase = ((unsigned long long)gb.y << 32) | gb.x;
+  I.p0 = ((unsigned long long)p0.y << 32) | p0.x;
+  I.boff = (long long)(((unsigned long long)bo.y << 32) | bo.x);
+  I.rem0 = rn.x;
+  I.nscan = rn.y;
+  I.staged = lds32(I32 + (uint32_t)offsetof(StageInfo, staged));
+  I.tail = lds32(I32 + (uint32_t)offsetof(StageInfo, tail));
+}
+// T = the whole tile in its stage buffer (plain stores scanned in place)
 __device__ __forceinline__ void tile_ctx(const StageInfo &I, uint32_t sb32, TileCtx &T) {
   T.sb32 = sb32;
-  T.p0 = I.p0;
+  T.gbase = I.gbase;
   T.boff = I.boff;
   T.rem0 = I.rem0;
   T.nscan = I.nscan;
@@ -952,26 +890,17 @@ __device__ __forceinline__ void tile_ctx(const StageInfo &I, uint32_t sb32, Tile
   T.tail = I.tail;
   T.first = I.p0 == 0;
 }
-
-struct SmemLayout {
-  SmemHeader *H;
-  uint8_t *ring;
-  uint32_t *g4s, *p23s, *staging;
-  uint16_t *q1;
-  unsigned long long *q2;
-};
-// header | ring | g4 | p23 | Q2 (8-byte entries) | staging | Q1
-template <bool HAS_G4, bool HAS_P23>
-__device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, uint32_t stages, uint32_t staging_words) {
-  SmemLayout L;
-  L.H = reinterpret_cast<SmemHeader *>(smem);
-  L.ring = smem + kSmemHeader;
-  L.g4s = reinterpret_cast<uint32_t *>(L.ring + (size_t)stages * kStageBytes);
-  L.p23s = L.g4s + (HAS_G4 ? P.st.g4_words : 0);
-  L.q2 = reinterpret_cast<unsigned long long *>(L.p23s + (HAS_P23 ? P.st.p23_words : 0));
-  L.staging = reinterpret_cast<uint32_t *>(L.q2 + kScanWarps * kQ2Entries);
-  L.q1 = reinterpret_cast<uint16_t *>(L.staging + staging_words);
-  return L;
+// T = chunk `cbase` of tile I in the warp's private buffer, as the matcher has to see it
+template <bool XF>
+__device__ __forceinline__ void build_chunk(const ScanParams &P, const StageInfo &I, uint32_t src32, uint32_t cbase,
+                                            uint32_t priv32, uint32_t xf32, uint32_t lane, TileCtx &T) {
+  if (XF && xf32) {
+    const uint32_t back = cbase + (I.boff >= (long long)kTilePre ? (uint32_t)kTilePre : (uint32_t)I.boff);
+    build_xf(P, I, src32, cbase, back, priv32, xf32, lane, T);
+  } else {
+    build_copy<XF>(I, src32, cbase, priv32, lane, T);
+  }
+  __syncwarp();
 }
 template <bool HAS_G4, bool HAS_P23>
 __device__ __forceinline__ void load_filters(const SmemLayout &L, const ScanParams &P, uint32_t tid, uint32_t nthreads) {
@@ -991,11 +920,11 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST>
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool XF>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t S = P.stages, cap = P.chunk_cap;
-  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, S, kScanWarps * cap);
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, (size_t)S * kStageBytes, kScanWarps * cap);
   SmemHeader &H = *L.H;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1062,7 +991,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 
   // ================================ scanning warps ================================
   // (everything in shared memory is addressed by 32-bit shared-space addresses from here on)
-  Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
+  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF> sc(P, L.g4s, L.p23s);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t ring32 = sbase + (uint32_t)(L.ring - smem);
   const uint32_t g4_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
@@ -1076,6 +1005,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   const uint32_t ctr32 = hdr32 + (uint32_t)offsetof(SmemHeader, chunk_ctr);
   const uint32_t endk32 = hdr32 + (uint32_t)offsetof(SmemHeader, end_k);
   const uint32_t info32 = hdr32 + (uint32_t)offsetof(SmemHeader, info);
+  // chunks are scanned in the stage buffer (plain stores, P.priv == 0) or in the warp's private
+  // buffer, which also is where case folding / normalisation happen (scan_device.cuh); with a private
+  // buffer the stage is handed back before the scan, so a slow chunk never holds up the ring
+  const bool priv_mode = XF || P.priv;
+  const uint32_t priv32 = sbase + (uint32_t)(L.priv - smem) + warp * (uint32_t)kPrivBytes;
+  if (XF && !(P.flags & kIdentityMap)) sc.xf32 = sbase + (uint32_t)(L.xf - smem) + warp * (uint32_t)kXfRowBytes;
   unsigned long long blk_next = 0; // this warp's block of temp[]: next free entry ...
   uint32_t blk_left = 0;           // ... and how many are left
   for (;;) {
@@ -1100,19 +1035,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     mbar_wait32(full32 + 8u * s, sp >> 16);
     const uint32_t tile = lds32(I32 + (uint32_t)offsetof(StageInfo, tile));
     if (tile == kNoTile) break;
-    TileCtx T;
-    {
-      const uint2 p0 = lds64(I32 + (uint32_t)offsetof(StageInfo, p0));
-      const uint2 bo = lds64(I32 + (uint32_t)offsetof(StageInfo, boff));
-      T.sb32 = ring32 + s * (uint32_t)kStageBytes;
-      T.p0 = ((unsigned long long)p0.y << 32) | p0.x;
-      T.boff = (long long)(((unsigned long long)bo.y << 32) | bo.x);
-      T.rem0 = lds32(I32 + (uint32_t)offsetof(StageInfo, rem0));
-      T.nscan = lds32(I32 + (uint32_t)offsetof(StageInfo, nscan));
-      T.staged = lds32(I32 + (uint32_t)offsetof(StageInfo, staged));
-      T.tail = lds32(I32 + (uint32_t)offsetof(StageInfo, tail));
-      T.first = (p0.x | p0.y) == 0;
-    }
+    StageInfo I;
+    load_info(I32, I);
+    const uint32_t stage_sb = ring32 + s * (uint32_t)kStageBytes;
     // (experiment knob OLM_GRAB: the kGrab chunks of a grab share the wait and the tile description)
 #if OLM_GRAB > 1
 #pragma unroll 1
@@ -1123,15 +1048,26 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 #endif
     const uint32_t cbase = ci * kChunkBytes;
     uint32_t n = 0, ovf = 0;
-    if (cbase < T.nscan) {
+    TileCtx T;
+    uint32_t cb = cbase; // position of the chunk inside T
+    bool work = cbase < I.nscan;
+    if (priv_mode) {
+      if (work) build_chunk<XF>(P, I, stage_sb + kTilePre + cbase, cbase, priv32, sc.xf32, lane, T);
+      __syncwarp();
+      if (lane == 0) mbar_arrive32(scanned32 + 8u * s); // the stage buffer is not read any more
+      cb = 0;
+      work = work && T.nscan != 0;
+    } else {
+      tile_ctx(I, stage_sb, T);
+    }
+    if (work) {
       if (FAST)
-        n = sc.template scan_chunk_fast<kStageMode>(T, T.sb32, g4_32, p23_32, q1_32, q2_32, cbase, lane, stage32, cap, 0,
-                                                    0, nullptr, &ovf);
+        n = sc.template scan_chunk_fast<kStageMode>(T, T.sb32, g4_32, p23_32, q1_32, q2_32, cb, lane, stage32, cap, 0, &ovf);
       else
-        n = sc.template scan_chunk<kStageMode>(T, cbase, lane, stage32, cap, q1_32, q2_32, 0, 0, nullptr, &ovf);
+        n = sc.template scan_chunk<kStageMode>(T, cb, lane, stage32, cap, q1_32, q2_32, 0, &ovf);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive32(scanned32 + 8u * s); // the stage buffer is not read any more
+    if (!priv_mode && lane == 0) mbar_arrive32(scanned32 + 8u * s); // the stage buffer is not read any more
     // ---- hand the chunk over: descriptor, and the staged matches into this warp's run of temp[]
     ovf = __any_sync(kFull, ovf != 0);
     ChunkDesc d;
@@ -1166,27 +1102,27 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 }
 
 // Chunks flagged kChunkOverflow (their matches did not fit the staging area): every warp takes
-// such chunks, copies the chunk (+ the bytes around it) into a small private buffer, evaluates
-// it again and writes final records at the index place_kernel left in the descriptor.
-constexpr int kRedoBuf = kTilePre + kChunkBytes + kTileHalo; // 640
-constexpr uint32_t kRedoStages = (kScanWarps * kRedoBuf + kStageBytes - 1) / kStageBytes; // "ring" space for the buffers
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS>
+// such chunks, reads the chunk's bytes (16 in front, kPrivData from its first byte on) from global
+// memory into a small stage of its own, builds its private buffer from that exactly like the main
+// pass, evaluates the chunk again and writes final records at the index the prefix pass computed.
+constexpr int kRedoStage = kTilePre + kPrivData;  // 656 bytes per warp
+constexpr size_t kRedoRingBytes = ((size_t)kScanWarps * kRedoStage + 127) & ~size_t(127);
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF>
 __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (*P.redo_flag == 0) return;
-  // header | "ring": one 640-byte buffer per warp | g4 | p23 | Q2 | Q1
-  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, kRedoStages, 0);
+  // header | one small stage per warp | g4 | p23 | Q2 | Q1 | private chunk buffers | rows
+  const SmemLayout L = carve<HAS_G4, HAS_P23>(smem, P, kRedoRingBytes, 0);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t fl = P.flags;
   load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
   __syncthreads();
   if (warp >= kScanWarps) return;
-  Scanner<HAS_G4, HAS_P23, HAS_CLS> sc(P, L.g4s, L.p23s);
+  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF> sc(P, L.g4s, L.p23s);
   sc.stat_inc = 0; // the main pass has counted these chunks already
-  uint16_t *my_q1 = L.q1 + warp * kChunkBytes;
-  unsigned long long *my_q2 = L.q2 + warp * kQ2Entries;
-  uint8_t *buf = L.ring + (size_t)warp * kRedoBuf;
-  const bool use_map = (fl & kWindowMode) && !(fl & kIdentityMap);
+  const uint32_t q1_32 = smem_u32(L.q1 + warp * kChunkBytes), q2_32 = smem_u32(L.q2 + warp * kQ2Entries);
+  uint8_t *buf = L.ring + (size_t)warp * kRedoStage;
+  const uint32_t priv32 = smem_u32(L.priv) + warp * (uint32_t)kPrivBytes;
+  if (XF && !(P.flags & kIdentityMap)) sc.xf32 = smem_u32(L.xf) + warp * (uint32_t)kXfRowBytes;
   const uint64_t n_chunks = (uint64_t)P.num_tiles * kTileChunks;
   // a warp looks at 32 descriptors at a time and takes the flagged chunks one after the other
   for (uint64_t c0 = ((uint64_t)blockIdx.x * kScanWarps + warp) * 32; c0 < n_chunks;
@@ -1201,21 +1137,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
       StageInfo I;
       fill_tile(P, tile, I);
       const uint32_t cbase = ci * kChunkBytes;
-      // the chunk as a tile of its own: position 0 = the chunk's first byte
-      TileCtx T;
-      T.sb32 = smem_u32(buf);
-      T.p0 = I.p0 + cbase;
-      T.boff = I.boff + cbase;
-      T.rem0 = I.rem0 - cbase;
-      T.nscan = I.nscan - cbase < (uint32_t)kChunkBytes ? I.nscan - cbase : (uint32_t)kChunkBytes;
-      T.staged = I.staged - cbase < (uint32_t)(kChunkBytes + kTileHalo) ? I.staged - cbase : (uint32_t)(kChunkBytes + kTileHalo);
-      T.tail = I.tail;
-      T.first = T.p0 == 0;
-      for (uint32_t i = lane; i < T.staged + kTilePre; i += 32) {
-        const long long src = T.boff - kTilePre + (long long)i;
-        buf[i] = src >= 0 ? P.buf[src] : 0;
+      { // what the tile's stage buffer would hold around the chunk
+        const long long first = I.boff + cbase - kTilePre;
+        uint32_t have = I.staged - cbase;
+        if (have > (uint32_t)kPrivData) have = kPrivData;
+        for (uint32_t i = lane; i < have + kTilePre; i += 32) buf[i] = first + (long long)i >= 0 ? P.buf[first + (long long)i] : 0;
       }
       __syncwarp();
+      TileCtx T;
+      build_chunk<XF>(P, I, smem_u32(buf) + kTilePre, cbase, priv32, sc.xf32, lane, T);
       // first result index: the span's base + the chunks before this one in the span
       unsigned long long base = P.span_base[ch / kPrefixSpan];
       {
@@ -1226,8 +1156,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
         for (int dd = 16; dd > 0; dd >>= 1) part += __shfl_xor_sync(kFull, part, dd);
         base += part;
       }
-      const uint32_t *map = use_map ? P.map + (size_t)I.win * kWindowBytes : nullptr;
-      sc.template scan_chunk<kDirectMode>(T, 0, lane, 0u, 0, smem_u32(my_q1), smem_u32(my_q2), base, I.emit_base, map, nullptr);
+      if (T.nscan) sc.template scan_chunk<kDirectMode>(T, 0, lane, 0u, 0, q1_32, q2_32, base, nullptr);
       __syncwarp();
     }
   }
@@ -1315,7 +1244,6 @@ __global__ void __launch_bounds__(kPrefixThreads) place_kernel(const __grid_cons
   }
   __syncthreads();
   const unsigned long long span0 = P.span_base[blockIdx.x];
-  const bool use_map = (P.flags & kWindowMode) && !(P.flags & kIdentityMap);
   for (uint32_t g0 = warp * 32; g0 < kPrefixSpan; g0 += (kPrefixThreads / 32) * 32) {
     const uint64_t ch = c0 + g0 + lane;
     uint2 d = make_uint2(0, 0);
@@ -1331,27 +1259,33 @@ __global__ void __launch_bounds__(kPrefixThreads) place_kernel(const __grid_cons
       const unsigned long long base = span0 + s_pre[g0 + src];
       StageInfo I;
       fill_tile(P, (uint32_t)(chs / kTileChunks), I);
-      const uint32_t *map = use_map ? P.map + (size_t)I.win * kWindowBytes : nullptr;
+      const unsigned long long cb = I.gbase + (chs % kTileChunks) * kChunkBytes; // global offset of the chunk's first byte
       for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t e = __ldg(P.temp + tb + i);
         const unsigned long long r = base + i;
-        if (r < P.out_cap)
-          put_record(P, r, I.emit_base, I.p0 + (e >> kPackLenBits), e & ((1u << kPackLenBits) - 1), map);
+        if (r < P.out_cap) put_record(P, r, cb + (e >> kPackLenBits), e & ((1u << kPackLenBits) - 1));
       }
     }
   }
 }
 
-template <bool G, bool Q, bool C>
+bool store_normalises(const DeviceStore &st) { return st.flags & (kFlagIgnorePunct | kFlagElideSpace); }
+
+size_t redo_smem_bytes(const DeviceStore &st) {
+  return kSmemHeader + kRedoRingBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kQ2Bytes + kQ1Bytes +
+         size_t(kScanWarps) * kPrivBytes + (store_normalises(st) ? size_t(kScanWarps) * kXfRowBytes : 0);
+}
+
+template <bool G, bool Q, bool C, bool XF>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
   const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
   // the lean per-candidate path covers every store, as long as no position predicate is requested
   constexpr bool can_fast = G || Q;
   const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
   if (fast)
-    scan_kernel<G, Q, C, can_fast><<<grid, kScanThreads, smem, stream>>>(p);
+    scan_kernel<G, Q, C, can_fast, XF><<<grid, kScanThreads, smem, stream>>>(p);
   else
-    scan_kernel<G, Q, C, false><<<grid, kScanThreads, smem, stream>>>(p);
+    scan_kernel<G, Q, C, false, XF><<<grid, kScanThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const uint64_t n_chunks = (uint64_t)p.num_tiles * kTileChunks;
@@ -1362,41 +1296,61 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   place_kernel<<<n_spans, kPrefixThreads, 0, stream>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  redo_kernel<G, Q, C><<<grid, kScanThreads, scan_smem_bytes(p.st, kRedoStages, 0), stream>>>(p);
+  redo_kernel<G, Q, C, XF><<<grid, kScanThreads, redo_smem_bytes(p.st), stream>>>(p);
   return cudaGetLastError();
 }
-
 template <bool G, bool Q, bool C>
+cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
+  if (p.flags & kWindowMode) return launch_variant<G, Q, C, true>(p, sms, smem, stream);
+  return launch_variant<G, Q, C, false>(p, sms, smem, stream);
+}
+
+template <bool G, bool Q, bool C, bool XF>
 cudaError_t configure_variant(size_t smem_limit) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
   if (e != cudaSuccess) return e;
   if (G || Q) {
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     if (e != cudaSuccess) return e;
   }
-  return cudaFuncSetAttribute(redo_kernel<G, Q, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  return cudaFuncSetAttribute(redo_kernel<G, Q, C, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+}
+template <bool G, bool Q, bool C>
+cudaError_t configure_variant(size_t smem_limit) {
+  const cudaError_t e = configure_variant<G, Q, C, false>(smem_limit);
+  return e != cudaSuccess ? e : configure_variant<G, Q, C, true>(smem_limit);
 }
 
 } // namespace
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap) {
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap, bool priv) {
   return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kQ2Bytes +
-         size_t(kScanWarps) * chunk_cap * 4 + kQ1Bytes;
+         size_t(kScanWarps) * chunk_cap * 4 + kQ1Bytes + (priv ? size_t(kScanWarps) * kPrivBytes : 0) +
+         (priv && store_normalises(st) ? size_t(kScanWarps) * kXfRowBytes : 0);
 }
 
-ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
+ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit, bool want_priv) {
   ScanGeometry g;
-  // the deepest ring that fits (refills track the warps more closely the more stages there are);
-  // whatever shared memory is left goes to the warps' staging areas (denser matches before a
-  // chunk has to be redone)
-  for (uint32_t s = kMaxStages; s >= 2; --s) {
-    if (scan_smem_bytes(st, s, kChunkCapMin) > smem_limit) continue;
-    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0);
-    uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
-    if (cap > kChunkCapMax) cap = kChunkCapMax;
-    g.stages = s;
-    g.chunk_cap = cap;
-    return g;
+  // Stores with a transform flag are always scanned in private chunk buffers (that is where they are
+  // folded / normalised); plain stores when asked to and when it fits.  With private buffers a stage
+  // is handed back as soon as its chunks are copied out, so a short ring is enough; without, the
+  // deepest ring that fits (refills track the warps more closely the more stages there are).
+  // Whatever shared memory is left goes to the warps' staging areas (denser matches before a chunk
+  // has to be redone).
+  const bool must_priv = st.flags & kFlagAnyTransform;
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool priv = must_priv || (want_priv && pass == 0);
+    for (uint32_t s = priv ? kPrivStagesMax : (uint32_t)kMaxStages; s >= 2; --s) {
+      if (scan_smem_bytes(st, s, kChunkCapMin, priv) > smem_limit) continue;
+      const size_t spare = smem_limit - scan_smem_bytes(st, s, 0, priv);
+      uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
+      if (cap > kChunkCapMax) cap = kChunkCapMax;
+      g.stages = s;
+      g.chunk_cap = cap;
+      g.priv = priv;
+      return g;
+    }
+    if (must_priv || !want_priv) break;
   }
   return g;
 }
@@ -1411,7 +1365,7 @@ cudaError_t scan_configure(size_t smem_limit) {
 }
 
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches) {
-  const size_t smem = scan_smem_bytes(p.st, p.stages, p.chunk_cap);
+  const size_t smem = scan_smem_bytes(p.st, p.stages, p.chunk_cap, p.priv || (p.flags & kWindowMode));
   const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0, c = g && !q && p.st.cls.run != 0;
   if (launches) *launches += 5;
   if (g && q) return launch_variant<true, true, false>(p, sms, smem, stream);

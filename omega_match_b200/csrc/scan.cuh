@@ -18,10 +18,12 @@ struct alignas(8) Record {
 };
 static_assert(sizeof(Record) == 24, "Record must match omega_match_result_t");
 
-// Per normalised window (stores with a transform flag).  Written by transform.cu on the device.
+// Per 4 MiB source window (stores with a transform flag).  Written by transform.cu on the device;
+// only launches that need it get one (case-folding-only stores: always, for norm_len; launches
+// with word_boundary over a store with 2..4 byte patterns: for the tail byte).
 struct WindowDesc {
   uint32_t norm_len; // M_w: bytes of the normalised window (after the trailing-space trim)
-  uint32_t extent;   // bytes written into the window's buffer (M_w, +1 if a space was trimmed)
+  uint32_t extent;   // bytes the reference writes into its scratch buffer (M_w, +1 if a space was trimmed)
   uint32_t tail;     // the byte the reference would read at index M_w
   uint32_t _pad;
 };
@@ -33,8 +35,8 @@ enum ScanFlags : uint32_t {
   kLineStart = 1u << 3,
   kLineEnd = 1u << 4,
   kLongestOnly = 1u << 5,
-  kWindowMode = 1u << 6,  // segments are normalised 4 MiB windows described by `windows`
-  kIdentityMap = 1u << 7, // window mode without an offset map (case folding only)
+  kWindowMode = 1u << 6,  // the store has a transform flag: 4 MiB source windows, normalised chunk by chunk inside the scan
+  kIdentityMap = 1u << 7, // window mode without compaction (case folding only)
   kCountAll = 1u << 8,    // exact statistics: count the short candidates kLongestOnly skips (stats.cuh)
 };
 
@@ -49,8 +51,8 @@ constexpr int kScanThreads = 1024;                  // + producer warp (31: tick
 #endif
 constexpr int kTileBytes = OLM_TILE_BYTES;          // positions per tile
 constexpr int kTilePre = 16;                        // bytes staged in front of a tile (previous byte)
-constexpr int kTileHalo = 112;                      // bytes staged behind a tile
-constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 8320 = 65*128
+constexpr int kTileHalo = 128;                      // bytes staged behind a tile
+constexpr int kStageBytes = kTilePre + kTileBytes + kTileHalo; // 4240
 constexpr int kChunkBytes = 512;                    // 32 lanes x 16 bytes: the unit a warp grabs
 constexpr int kTileChunks = kTileBytes / kChunkBytes; // 16
 constexpr int kMaxStages = OLM_MAX_STAGES;          // ring of tile buffers (a power of two >= 2)
@@ -61,7 +63,14 @@ constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 
 constexpr int kQ2Entries = 96;                      // hit queue per warp (u64 entries): 31 left over + 2 x 32 new
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
 constexpr int kSmemHeader = 16 * kMaxStages + 64 * kInfoRing + 256; // barriers, counters, stage infos (a multiple of 128)
-constexpr uint32_t kPackLenBits = 18;               // staged entry = pos_in_tile << 18 | len
+constexpr uint32_t kPackLenBits = 23;               // staged entry = pos_in_chunk << 23 | len (source coordinates)
+// Private chunk buffer of a scanning warp: the chunk's bytes as the matcher sees them (copied,
+// case-folded or normalised), 16 bytes in front of position 0 and up to kPrivData bytes from it on.
+constexpr int kChunkHalo = 112;                     // plain / case-folded chunks: bytes copied behind the 512 positions
+constexpr int kPrivData = 640;                      // normalised chunks: at most 512 + 128 source bytes
+constexpr int kPrivBytes = kTilePre + kPrivData + 48; // 704 (16-byte units; the hash of the last positions reads past the data)
+constexpr int kXfRowBytes = 128 + kPrivData;        // per warp: state of a normalised chunk (scan_device.cuh): walk state, source offset - index of every byte
+constexpr uint32_t kRemUnknown = 0x40000000u;       // normalised chunk that does not reach its window's end
 constexpr uint32_t kChunkOverflow = 0x80000000u;    // ChunkDesc::count flag: records are written by redo_kernel
 constexpr uint32_t kPrefixSpan = 4096;              // chunks per block of the prefix / place kernels
 
@@ -76,13 +85,14 @@ struct ScanParams {
   uint64_t scan_begin; // first owned start position (multiple of 16)
   uint64_t scan_end;   // one past the last owned start position
   uint32_t tail_byte;  // value assumed at position seg_len (plain mode)
-  // window mode
-  const WindowDesc *windows;
-  const uint32_t *map;   // per window: kWindowBytes entries, normalised index -> source index
-  uint64_t win_stride;   // bytes between normalised windows in buf
-  uint64_t win_buf_off;  // buffer offset of window 0
-  uint64_t win_src_base; // source offset of window 0 (global)
+  // window mode (the store has a transform flag): buf holds SOURCE bytes, tiles are 4 KiB of one window
+  const WindowDesc *windows; // per window of the launch, or nullptr (see WindowDesc)
+  uint64_t win_buf_off;  // buffer offset of the first source byte of window 0
+  uint64_t win_src_base; // global source offset of window 0
+  uint64_t win_src_len;  // source bytes of the launch's windows (the last one may be short)
   uint32_t tiles_per_win;
+  uint32_t store_flags;  // kFlagIgnoreCase | kFlagIgnorePunct | kFlagElideSpace of the store
+  uint32_t priv;         // plain stores: 1 = chunks are copied into the warp's private buffer before the scan
   // tiles
   uint32_t num_tiles;             // tiles of this launch
   ChunkDesc *chunk_desc;          // [num_tiles * kTileChunks] written by the scan
@@ -115,12 +125,14 @@ inline uint64_t temp_slack_entries(int sms) { return uint64_t(sms) * kScanWarps 
 
 struct ScanGeometry {
   uint32_t stages = 0, chunk_cap = 0;
+  bool priv = false; // chunks are scanned in the warps' private buffers
 };
+constexpr uint32_t kPrivStagesMax = 6; // ring depth with private chunk buffers
 
-size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap);
+size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap, bool priv);
 // chooses ring depth and staging capacity for the shared memory there is; stages == 0 if the
 // filters do not fit at all
-ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit);
+ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit, bool want_priv);
 // scan -> prefix over the chunk counts (two kernels) -> placement of the records in final order
 // -> redo pass (exits at once when no chunk overflowed)
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches);

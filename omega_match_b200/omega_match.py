@@ -145,13 +145,20 @@ class Matcher:
 
     def __init__(self, compiled_or_patterns_file: str, case_insensitive: bool = False,
                  ignore_punctuation: bool = False, elide_whitespace: bool = False,
-                 device: Optional[int] = None) -> None:
+                 device: Optional[int] = None, devices: Optional[List[int]] = None) -> None:
+        """`devices` (B200 extension): several GPUs in this process -- match() shards every haystack by
+        byte range over them (include/olm_b200.h olm_cuda_matcher_create_multi; compiled stores only)."""
         self._lib = _lib.load()
+        self._comm = None
         if device is not None:
             self._lib.olm_cuda_set_default_device(int(device))
         st = PatternStoreStatsC()
-        m = self._lib.omega_list_matcher_create(compiled_or_patterns_file.encode("utf-8"), int(case_insensitive),
-                                                int(ignore_punctuation), int(elide_whitespace), C.byref(st))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            m = self._lib.olm_cuda_matcher_create_multi(compiled_or_patterns_file.encode("utf-8"), arr, len(devices))
+        else:
+            m = self._lib.omega_list_matcher_create(compiled_or_patterns_file.encode("utf-8"), int(case_insensitive),
+                                                    int(ignore_punctuation), int(elide_whitespace), C.byref(st))
         if not m:
             raise RuntimeError("Failed to create matcher")
         self._matcher = m
@@ -209,6 +216,9 @@ class Matcher:
         return self._lib.omega_matcher_get_chunk_size(self._matcher)
 
     def destroy(self) -> None:
+        if getattr(self, "_comm", None):
+            self._lib.olm_cuda_comm_destroy(self._comm)
+            self._comm = None
         if getattr(self, "_matcher", None):
             self._lib.omega_list_matcher_destroy(self._matcher)
             self._matcher = None
@@ -275,6 +285,39 @@ class Matcher:
                                                global_size, match_ptr_base, *f, C.byref(res)) != 0:
             raise RuntimeError("olm_cuda_match_shard_host failed (see stderr)")
         return int(res.count), int(res.records or 0)
+
+    # -- one process per GPU: the library's own NCCL gather (include/olm_b200.h) ---------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0: the 128-byte id every rank of the job passes to comm_init()."""
+        buf = C.create_string_buffer(128)
+        if _lib.load().olm_cuda_comm_unique_id(buf, 128) != 0:
+            raise RuntimeError("olm_cuda_comm_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._comm = self._lib.olm_cuda_comm_create(self._matcher, buf, rank, world)
+        if not self._comm:
+            raise RuntimeError("olm_cuda_comm_create failed")
+
+    def gather_records(self, records_ptr: int, count: int, root: int = 0, no_overlap: bool = False):
+        """Collective: the ranks' sorted records -> (count, device pointer) of the whole on `root`
+        ((0, 0) on the other ranks)."""
+        res = CudaResultsC()
+        if self._lib.olm_cuda_gather_records(self._comm, records_ptr, count, root, int(no_overlap), C.byref(res)) != 0:
+            raise RuntimeError("olm_cuda_gather_records failed (see stderr)")
+        return int(res.count), int(res.records or 0)
+
+    def shard_plan(self, global_size: int, world: int, rank: int):
+        sh = _lib.ShardC()
+        if self._lib.olm_cuda_shard_plan(self._matcher, global_size, world, rank, C.byref(sh)) != 0:
+            raise RuntimeError("olm_cuda_shard_plan failed")
+        return sh.own_begin, sh.own_end, sh.slice_begin, sh.slice_end
+
+    @property
+    def device_count(self) -> int:
+        return self._lib.olm_cuda_matcher_device_count(self._matcher)
 
     def no_overlap_device(self, records_ptr: int, count: int) -> int:
         n = self._lib.olm_cuda_no_overlap(self._matcher, records_ptr, count)

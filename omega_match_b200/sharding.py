@@ -39,21 +39,20 @@ class Shard:
 
 
 def shard_plan(size: int, world: int, largest_pattern: int, windowed: bool) -> List[Shard]:
-    """Split [0, size) into `world` contiguous ownership ranges plus the bytes each rank must hold."""
+    """Split [0, size) into `world` contiguous ownership ranges plus the bytes each rank must hold:
+    the library's own plan (include/olm_b200.h olm_shard_plan), the one its multi-GPU matcher uses."""
     if world < 1:
         raise ValueError("world must be >= 1")
-    unit = WINDOW if windowed else 4096
-    units = (size + unit - 1) // unit
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
     shards = []
     for r in range(world):
-        b = min(size, (units * r // world) * unit)
-        e = min(size, (units * (r + 1) // world) * unit) if r + 1 < world else size
-        if windowed:
-            sb, se = b, e
-        else:
-            sb = max(0, b - ALIGN)
-            se = min(size, e + largest_pattern + 1)
-        shards.append(Shard(r, b, e, sb, se))
+        sh = _lib.ShardC()
+        if lib.olm_shard_plan(largest_pattern, int(bool(windowed)), size, world, r, C.byref(sh)) != 0:
+            raise RuntimeError("olm_shard_plan failed")
+        shards.append(Shard(r, sh.own_begin, sh.own_end, sh.slice_begin, sh.slice_end))
     return shards
 
 
