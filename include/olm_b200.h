@@ -172,9 +172,7 @@ typedef struct {
  *                             range over them (see olm_cuda_matcher_create_multi)
  *   OLM_EXACT_STATS=1         see olm_cuda_set_exact_stats
  *   OLM_HOST_SPAN_BYTES=<n>   omega_list_matcher_match scans host haystacks longer than n bytes in
- *                             spans of n bytes (bounded device memory; same results)
- *   OLM_PRIV=0                plain stores: scan chunks in the staged tile instead of a private
- *                             copy per warp (a tuning knob; same results) */
+ *                             spans of n bytes (bounded device memory; same results) */
 int olm_cuda_device_count(void);
 /* Choose the GPU a matcher lives on BEFORE create (process wide default: device 0 or
  * $OLM_CUDA_DEVICE). */

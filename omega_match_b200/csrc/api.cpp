@@ -227,6 +227,7 @@ int omega_matcher_set_num_threads(omega_list_matcher_t *m, int threads) {
   if (threads == 0) threads = mx;
   else if (threads < 0 || threads > mx) return -1;
   m->threads = threads;
+  if (m->engine && !m->multi) m->engine->set_host_threads(threads); // staging of pageable haystacks (engine.cu Stager)
   return 0;
 }
 int omega_matcher_get_num_threads(const omega_list_matcher_t *m) { return m ? m->threads : -1; }

@@ -17,9 +17,14 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -82,21 +87,43 @@ int upload(DevBuf &b, const std::vector<T> &v, const T **out) {
 
 } // namespace
 
+// Pageable host haystacks (main.c maps the file, the cffi wrapper copies into ordinary memory): a
+// plain cudaMemcpyAsync from such memory is a synchronous, single-threaded staged copy with no
+// overlap.  Instead worker threads copy 8 MiB pieces into the engine's own pinned slots and issue
+// the H2D copies from there, so that the CPU copy of one piece, the DMA of others and the scan of
+// the segments that are complete all run at once.
+constexpr size_t kPieceBytes = size_t(8) << 20;
+struct Stager {
+  std::vector<std::thread> workers;
+  std::vector<uint8_t *> slots;          // 2 per worker, pinned
+  std::vector<cudaEvent_t> slot_events;  // the slot's last copy has finished
+  std::unique_ptr<std::atomic<int>[]> seg_left; // pieces of a segment not issued yet
+  std::atomic<uint64_t> next_piece{0};
+  std::atomic<int> failed{0};
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<char> recorded;            // seg_events[i] has been recorded (guarded by mu)
+  bool active = false;
+};
+
 struct EngineImpl {
   int device = 0, sms = 0;
+  int host_threads = 4;
+  Stager stager;
   size_t smem_limit = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   // host path: the haystack arrives in segments; seg_events[i] fires when bytes
   // [0, (i+1) * seg_bytes) are in HBM (empty = everything is resident already)
   std::vector<cudaEvent_t> seg_events;
   uint64_t seg_bytes = 0;
+  size_t seg_waited = 0; // segment events of this call the stream already waits for
   bool streaming = false; // set by match_host around its call of match_device
   Header hdr;
   DeviceStore ds;
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, tfvisible, misc, windows, ghost, fscratch, gather;
+  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, tfvisible, tfplan, tfextent, misc, windows, ghost, fscratch, gather;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -119,6 +146,23 @@ namespace {
 size_t seg_event_for(const EngineImpl &E, uint64_t bytes) {
   if (E.seg_events.size() <= 1 || E.seg_bytes == 0 || bytes == 0) return 0;
   return std::min<size_t>(E.seg_events.size() - 1, size_t((bytes - 1) / E.seg_bytes));
+}
+// The stream may only wait on a segment event that HAS been recorded: with staging threads at work
+// the host first waits until the segment's last piece has been issued.
+// (Staged pieces are issued by several threads: a later segment's event does not imply the earlier
+// ones, so every segment up to idx is waited for once.)
+int wait_segment(EngineImpl &E, size_t idx) {
+  Stager &S = E.stager;
+  for (size_t j = std::min(E.seg_waited, idx); j <= idx; ++j) {
+    if (S.active) {
+      std::unique_lock<std::mutex> lk(S.mu);
+      S.cv.wait(lk, [&] { return S.recorded[j] || S.failed.load(); });
+      if (S.failed.load()) return -1;
+    }
+    if (cudaStreamWaitEvent(E.stream, E.seg_events[j], 0) != cudaSuccess) return -1;
+  }
+  E.seg_waited = std::max(E.seg_waited, idx + 1);
+  return 0;
 }
 } // namespace
 
@@ -194,11 +238,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && cudaStreamCreateWithFlags(&impl->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
   ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
-  {
-    // plain stores: scan chunks in private buffers (the ring is handed back before the scan) unless OLM_PRIV=0
-    const char *pv = std::getenv("OLM_PRIV");
-    impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit, !(pv && pv[0] == '0'));
-  }
+  impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit);
   if (!ok || impl->geo.stages == 0) {
     delete eng;
     return fail("CUDA setup failed while uploading the store");
@@ -217,13 +257,15 @@ Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
-                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->tfvisible, &impl_->misc,
+                    &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->tfvisible, &impl_->tfplan, &impl_->tfextent, &impl_->misc,
                     &impl_->windows, &impl_->gather, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
                     &impl_->d_slens})
     b->release();
   for (auto &ev : impl_->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : impl_->seg_events) cudaEventDestroy(ev);
+  for (auto &ev : impl_->stager.slot_events) cudaEventDestroy(ev);
+  for (uint8_t *p : impl_->stager.slots) cudaFreeHost(p);
   if (impl_->stream) cudaStreamDestroy(impl_->stream);
   if (impl_->copy_stream) cudaStreamDestroy(impl_->copy_stream);
   delete impl_;
@@ -304,13 +346,22 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
   const bool identity_map = windowed && !(E.hdr.flags & (kFlagIgnorePunct | kFlagElideSpace));
   // window descriptors: case-folding-only stores need the trimmed window lengths, stores with
   // 2..4 byte patterns the stale-tail bytes (transform.cu)
+  // The stale-tail bytes are read only under word_boundary (matcher.c:812-848), but the image of the
+  // scratch buffer has to follow EVERY call.  Stores that drop bytes: with word_boundary the
+  // descriptors are computed before the scan (one more pass over the source); without, the scan
+  // counts the window extents as it goes and only the image is updated afterwards.
   const bool need_tails = windowed && E.has_short_234;
-  const bool need_desc = windowed && (identity_map || need_tails);
-  if (need_desc) {
+  const bool ghost_after = need_tails && !identity_map && !f.word_boundary;
+  const bool need_desc = windowed && (identity_map || (need_tails && !ghost_after));
+  if (need_desc || ghost_after) {
     const uint64_t bw = std::min<uint64_t>(n_windows, kBatchWindows);
-    if (E.windows.ensure(n_windows * sizeof(WindowDesc))) return -1;
-    if (!identity_map && E.tfblocks.ensure(bw * kTfBlocksPerWindow * sizeof(TfBlock))) return -1;
-    if (!identity_map && E.tfvisible.ensure(bw * sizeof(uint2))) return -1;
+    if (need_desc && E.windows.ensure(n_windows * sizeof(WindowDesc))) return -1;
+    if (!identity_map) {
+      if (E.tfblocks.ensure(bw * kTfBlocksPerWindow * sizeof(TfBlock))) return -1;
+      if (E.tfvisible.ensure(bw * sizeof(uint2))) return -1;
+      if (E.tfplan.ensure(bw * sizeof(uint4))) return -1;
+      if (E.tfextent.ensure(bw * sizeof(uint32_t))) return -1;
+    }
   }
 
   uint64_t cap = std::max<uint64_t>(E.out_hint, n_own / 64 + 4096);
@@ -360,7 +411,6 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
     P.flags = fl;
     P.stages = E.geo.stages;
     P.chunk_cap = E.geo.chunk_cap;
-    P.priv = E.geo.priv;
     P.store_flags = E.hdr.flags;
     P.tail_byte = 0;
 
@@ -377,7 +427,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.redo_flag = d_redo_flags + b;
         if (E.streaming) { // the scan reads a halo past its positions: the copy has to be that far
           const uint64_t upto = std::min<uint64_t>(r.slice_len, P.scan_end - r.slice_begin + kTileHalo + 16);
-          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[seg_event_for(E, upto)], 0));
+          if (wait_segment(E, seg_event_for(E, upto))) return -1;
         }
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
         if (E.want_stats) OLM_CUDA(stats_launch(P, E.stats, d_stats, E.sms, E.stream, &launches));
@@ -389,7 +439,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         const uint32_t nw = (uint32_t)std::min<uint64_t>(kBatchWindows, n_windows - w0);
         if (E.streaming) { // source bytes of this batch of windows
           const uint64_t src_end = std::min<uint64_t>(n_own, (w0 + nw) * uint64_t(kWindowBytes));
-          OLM_CUDA(cudaStreamWaitEvent(E.stream, E.seg_events[seg_event_for(E, (r.own_begin - r.slice_begin) + src_end)], 0));
+          if (wait_segment(E, seg_event_for(E, (r.own_begin - r.slice_begin) + src_end))) return -1;
         }
         P.buf = static_cast<const uint8_t *>(r.dev);
         P.buf_len = (r.slice_len + 15) & ~uint64_t(15);
@@ -397,16 +447,22 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.win_src_base = r.own_begin + w0 * kWindowBytes;
         P.win_src_len = std::min<uint64_t>(uint64_t(nw) * kWindowBytes, n_own - w0 * kWindowBytes);
         P.windows = nullptr;
+        P.win_extent = nullptr;
+        TransformParams T{};
+        T.src = P.buf;
+        T.src_off = P.win_buf_off;
+        T.src_len = P.win_src_len;
+        T.windows = need_desc ? static_cast<WindowDesc *>(E.windows.p) + w0 : nullptr;
+        T.blocks = static_cast<TfBlock *>(E.tfblocks.p);
+        T.visible = static_cast<uint2 *>(E.tfvisible.p);
+        T.plan = static_cast<uint4 *>(E.tfplan.p);
+        T.ghost = static_cast<uint8_t *>(E.ghost.p);
+        T.flags = E.hdr.flags;
+        if (ghost_after) {
+          P.win_extent = static_cast<uint32_t *>(E.tfextent.p);
+          OLM_CUDA(cudaMemsetAsync(P.win_extent, 0, nw * sizeof(uint32_t), E.stream));
+        }
         if (need_desc) {
-          TransformParams T{};
-          T.src = P.buf;
-          T.src_off = P.win_buf_off;
-          T.src_len = P.win_src_len;
-          T.windows = static_cast<WindowDesc *>(E.windows.p) + w0;
-          T.blocks = static_cast<TfBlock *>(E.tfblocks.p);
-          T.visible = static_cast<uint2 *>(E.tfvisible.p);
-          T.ghost = static_cast<uint8_t *>(E.ghost.p);
-          T.flags = E.hdr.flags;
           OLM_CUDA(cudaEventRecord(E.ev[2], E.stream));
           OLM_CUDA(window_descs_launch(T, nw, need_tails, E.sms, E.stream, &launches));
           OLM_CUDA(cudaEventRecord(E.ev[3], E.stream));
@@ -418,6 +474,7 @@ int Engine::match_device(const ScanRange &r, const MatchFlags &f, olm_cuda_resul
         P.ticket = d_tickets + b;
         P.redo_flag = d_redo_flags + b;
         OLM_CUDA(scan_launch(P, E.sms, E.stream, &launches));
+        if (ghost_after) OLM_CUDA(ghost_update_launch(T, nw, P.win_extent, E.sms, E.stream, &launches));
         if (E.want_stats) OLM_CUDA(stats_launch(P, E.stats, d_stats, E.sms, E.stream, &launches));
         ++scan_launches;
       }
@@ -500,7 +557,15 @@ int Engine::stage_host(const uint8_t *src, size_t n) {
     E.seg_events.pop_back();
   }
   E.seg_bytes = nseg > 1 ? kSegmentBytes : 0;
+  E.seg_waited = 0;
   OLM_CUDA(cudaEventRecord(E.ev[4], E.copy_stream));
+  {
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (!pinned && n >= 4 * kPieceBytes) return stage_pageable(src, n, nseg);
+  }
   for (uint64_t i = 0; i < nseg; ++i) {
     const uint64_t b = i * kSegmentBytes, e = nseg > 1 ? std::min<uint64_t>(n, b + kSegmentBytes) : n;
     OLM_CUDA(cudaMemcpyAsync(static_cast<uint8_t *>(E.hay.p) + b, src + b, e - b, cudaMemcpyHostToDevice, E.copy_stream));
@@ -509,6 +574,76 @@ int Engine::stage_host(const uint8_t *src, size_t n) {
   OLM_CUDA(cudaEventRecord(E.ev[5], E.copy_stream));
   return 0;
 }
+
+// Pageable memory: see Stager.  Returns after the workers have been started; match_device() waits
+// for a segment's event to be recorded before it lets the stream wait on it, finish_staging() joins.
+int Engine::stage_pageable(const uint8_t *src, size_t n, uint64_t nseg) {
+  EngineImpl &E = *impl_;
+  Stager &S = E.stager;
+  const uint64_t n_pieces = (n + kPieceBytes - 1) / kPieceBytes;
+  const uint64_t per_seg = nseg > 1 ? kSegmentBytes / kPieceBytes : n_pieces;
+  const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)E.host_threads, 8, n_pieces}));
+  while (S.slots.size() < size_t(2 * T)) {
+    uint8_t *p = nullptr;
+    cudaEvent_t ev;
+    OLM_CUDA(cudaHostAlloc(&p, kPieceBytes, cudaHostAllocDefault));
+    OLM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    S.slots.push_back(p);
+    S.slot_events.push_back(ev);
+  }
+  S.seg_left.reset(new std::atomic<int>[nseg]);
+  for (uint64_t i = 0; i < nseg; ++i) {
+    const uint64_t first = i * per_seg, last = std::min<uint64_t>(n_pieces, first + per_seg);
+    S.seg_left[i].store((int)(last - first));
+  }
+  S.recorded.assign(nseg, 0);
+  S.next_piece.store(0);
+  S.failed.store(0);
+  S.active = true;
+  uint8_t *dst = static_cast<uint8_t *>(E.hay.p);
+  for (int t = 0; t < T; ++t) {
+    S.workers.emplace_back([&E, &S, src, dst, n, n_pieces, per_seg, nseg, t]() {
+      if (cudaSetDevice(E.device) != cudaSuccess) S.failed.store(1);
+      for (uint32_t use = 0; !S.failed.load(); ++use) {
+        const uint64_t p = S.next_piece.fetch_add(1);
+        if (p >= n_pieces) break;
+        const size_t slot = size_t(2 * t) + (use & 1u);
+        const uint64_t b = p * kPieceBytes, len = std::min<uint64_t>(kPieceBytes, n - b);
+        bool ok = cudaEventSynchronize(S.slot_events[slot]) == cudaSuccess; // (never recorded: returns at once)
+        if (ok) {
+          std::memcpy(S.slots[slot], src + b, len);
+          ok = cudaMemcpyAsync(dst + b, S.slots[slot], len, cudaMemcpyHostToDevice, E.copy_stream) == cudaSuccess &&
+               cudaEventRecord(S.slot_events[slot], E.copy_stream) == cudaSuccess;
+        }
+        const uint64_t seg = std::min<uint64_t>(nseg - 1, p / per_seg);
+        if (ok && S.seg_left[seg].fetch_sub(1) == 1) { // the segment's last piece: every copy of it has been issued
+          ok = cudaEventRecord(E.seg_events[seg], E.copy_stream) == cudaSuccess;
+          if (ok && seg == nseg - 1) ok = cudaEventRecord(E.ev[5], E.copy_stream) == cudaSuccess;
+          std::lock_guard<std::mutex> lk(S.mu);
+          S.recorded[seg] = 1;
+          S.cv.notify_all();
+        }
+        if (!ok) {
+          S.failed.store(1);
+          std::lock_guard<std::mutex> lk(S.mu);
+          S.cv.notify_all();
+        }
+      }
+    });
+  }
+  return 0;
+}
+
+int Engine::finish_staging() {
+  Stager &S = impl_->stager;
+  if (!S.active) return 0;
+  for (auto &t : S.workers) t.join();
+  S.workers.clear();
+  S.active = false;
+  return S.failed.load() ? -1 : 0;
+}
+
+void Engine::set_host_threads(int n) { impl_->host_threads = n < 1 ? 1 : n; }
 
 namespace {
 struct StreamingScope { // the device-resident entry points never see segments
@@ -529,7 +664,8 @@ int Engine::match_shard_host(const uint8_t *host_slice, const ScanRange &range, 
   StreamingScope scope(E);
   ScanRange r = range;
   r.dev = E.hay.p;
-  if (match_device(r, f, out) != 0) return -1;
+  const int rc = match_device(r, f, out);
+  if (finish_staging() != 0 || rc != 0) return -1;
   float ms = 0.f;
   OLM_CUDA(cudaStreamSynchronize(E.copy_stream));
   cudaEventElapsedTime(&ms, E.ev[4], E.ev[5]);

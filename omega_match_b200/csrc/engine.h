@@ -63,10 +63,14 @@ public:
   // While on, every call also runs stats_kernel (stats.cuh) so that collect_stats() reports the
   // reference's counters exactly; off (default): the scan's own counters, no extra kernel.
   void set_exact_stats(bool on);
+  // host threads that stage PAGEABLE haystacks through pinned memory (omega_matcher_set_num_threads)
+  void set_host_threads(int n);
 
 private:
   Engine() = default;
   int stage_host(const uint8_t *src, size_t n);
+  int stage_pageable(const uint8_t *src, size_t n, uint64_t nseg);
+  int finish_staging();
   omega_match_results_t *match_host_spans(const uint8_t *haystack, size_t n, const MatchFlags &f, uint64_t span);
   EngineImpl *impl_ = nullptr;
 };

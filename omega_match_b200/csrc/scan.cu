@@ -876,8 +876,10 @@ __device__ __forceinline__ void load_info(uint32_t I32, StageInfo &I) {
   I.boff = (long long)(((unsigned long long)bo.y << 32) | bo.x);
   I.rem0 = rn.x;
   I.nscan = rn.y;
+  const uint2 tw = lds64(I32 + (uint32_t)offsetof(StageInfo, tail));
+  I.tail = tw.x;
+  I.win = tw.y;
   I.staged = lds32(I32 + (uint32_t)offsetof(StageInfo, staged));
-  I.tail = lds32(I32 + (uint32_t)offsetof(StageInfo, tail));
 }
 // T = the whole tile in its stage buffer (plain stores scanned in place)
 __device__ __forceinline__ void tile_ctx(const StageInfo &I, uint32_t sb32, TileCtx &T) {
@@ -893,10 +895,10 @@ __device__ __forceinline__ void tile_ctx(const StageInfo &I, uint32_t sb32, Tile
 // T = chunk `cbase` of tile I in the warp's private buffer, as the matcher has to see it
 template <bool XF>
 __device__ __forceinline__ void build_chunk(const ScanParams &P, const StageInfo &I, uint32_t src32, uint32_t cbase,
-                                            uint32_t priv32, uint32_t xf32, uint32_t lane, TileCtx &T) {
+                                            uint32_t priv32, uint32_t xf32, uint32_t lane, bool first_pass, TileCtx &T) {
   if (XF && xf32) {
     const uint32_t back = cbase + (I.boff >= (long long)kTilePre ? (uint32_t)kTilePre : (uint32_t)I.boff);
-    build_xf(P, I, src32, cbase, back, priv32, xf32, lane, T);
+    build_xf(P, I, src32, cbase, back, priv32, xf32, lane, first_pass, T);
   } else {
     build_copy<XF>(I, src32, cbase, priv32, lane, T);
   }
@@ -1005,10 +1007,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   const uint32_t ctr32 = hdr32 + (uint32_t)offsetof(SmemHeader, chunk_ctr);
   const uint32_t endk32 = hdr32 + (uint32_t)offsetof(SmemHeader, end_k);
   const uint32_t info32 = hdr32 + (uint32_t)offsetof(SmemHeader, info);
-  // chunks are scanned in the stage buffer (plain stores, P.priv == 0) or in the warp's private
-  // buffer, which also is where case folding / normalisation happen (scan_device.cuh); with a private
-  // buffer the stage is handed back before the scan, so a slow chunk never holds up the ring
-  const bool priv_mode = XF || P.priv;
+  // plain stores are scanned in the stage buffer; stores with a transform flag in the warp's private
+  // buffer, which is where case folding / normalisation happen (scan_device.cuh) -- the stage is
+  // handed back before the scan then.  (Private copies for plain stores were measured too: 555 vs
+  // 581 GB/s at 1 M patterns, 316 vs 336 on the short-pattern store, 338 vs 322 on names.txt.)
+  constexpr bool priv_mode = XF;
   const uint32_t priv32 = sbase + (uint32_t)(L.priv - smem) + warp * (uint32_t)kPrivBytes;
   if (XF && !(P.flags & kIdentityMap)) sc.xf32 = sbase + (uint32_t)(L.xf - smem) + warp * (uint32_t)kXfRowBytes;
   unsigned long long blk_next = 0; // this warp's block of temp[]: next free entry ...
@@ -1052,7 +1055,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     uint32_t cb = cbase; // position of the chunk inside T
     bool work = cbase < I.nscan;
     if (priv_mode) {
-      if (work) build_chunk<XF>(P, I, stage_sb + kTilePre + cbase, cbase, priv32, sc.xf32, lane, T);
+      if (work) build_chunk<XF>(P, I, stage_sb + kTilePre + cbase, cbase, priv32, sc.xf32, lane, true, T);
       __syncwarp();
       if (lane == 0) mbar_arrive32(scanned32 + 8u * s); // the stage buffer is not read any more
       cb = 0;
@@ -1145,7 +1148,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
       }
       __syncwarp();
       TileCtx T;
-      build_chunk<XF>(P, I, smem_u32(buf) + kTilePre, cbase, priv32, sc.xf32, lane, T);
+      build_chunk<XF>(P, I, smem_u32(buf) + kTilePre, cbase, priv32, sc.xf32, lane, false, T);
       // first result index: the span's base + the chunks before this one in the span
       unsigned long long base = P.span_base[ch / kPrefixSpan];
       {
@@ -1329,28 +1332,22 @@ size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_ca
          (priv && store_normalises(st) ? size_t(kScanWarps) * kXfRowBytes : 0);
 }
 
-ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit, bool want_priv) {
+ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit) {
   ScanGeometry g;
-  // Stores with a transform flag are always scanned in private chunk buffers (that is where they are
-  // folded / normalised); plain stores when asked to and when it fits.  With private buffers a stage
-  // is handed back as soon as its chunks are copied out, so a short ring is enough; without, the
-  // deepest ring that fits (refills track the warps more closely the more stages there are).
-  // Whatever shared memory is left goes to the warps' staging areas (denser matches before a chunk
-  // has to be redone).
-  const bool must_priv = st.flags & kFlagAnyTransform;
-  for (int pass = 0; pass < 2; ++pass) {
-    const bool priv = must_priv || (want_priv && pass == 0);
-    for (uint32_t s = priv ? kPrivStagesMax : (uint32_t)kMaxStages; s >= 2; --s) {
-      if (scan_smem_bytes(st, s, kChunkCapMin, priv) > smem_limit) continue;
-      const size_t spare = smem_limit - scan_smem_bytes(st, s, 0, priv);
-      uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
-      if (cap > kChunkCapMax) cap = kChunkCapMax;
-      g.stages = s;
-      g.chunk_cap = cap;
-      g.priv = priv;
-      return g;
-    }
-    if (must_priv || !want_priv) break;
+  // Stores with a transform flag are scanned in private chunk buffers (that is where they are folded
+  // / normalised): a stage is handed back as soon as its chunks are copied out, so a short ring is
+  // enough.  Plain stores are scanned in place: the deepest ring that fits (refills track the warps
+  // more closely the more stages there are).  Whatever shared memory is left goes to the warps'
+  // staging areas (denser matches before a chunk has to be redone).
+  const bool priv = st.flags & kFlagAnyTransform;
+  for (uint32_t s = priv ? kPrivStagesMax : (uint32_t)kMaxStages; s >= 2; --s) {
+    if (scan_smem_bytes(st, s, kChunkCapMin, priv) > smem_limit) continue;
+    const size_t spare = smem_limit - scan_smem_bytes(st, s, 0, priv);
+    uint32_t cap = uint32_t(spare / (size_t(kScanWarps) * 4)) & ~7u;
+    if (cap > kChunkCapMax) cap = kChunkCapMax;
+    g.stages = s;
+    g.chunk_cap = cap;
+    return g;
   }
   return g;
 }
@@ -1365,7 +1362,7 @@ cudaError_t scan_configure(size_t smem_limit) {
 }
 
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches) {
-  const size_t smem = scan_smem_bytes(p.st, p.stages, p.chunk_cap, p.priv || (p.flags & kWindowMode));
+  const size_t smem = scan_smem_bytes(p.st, p.stages, p.chunk_cap, (p.flags & kWindowMode) != 0);
   const bool g = p.st.g4_words != 0, q = p.st.p23_words != 0, c = g && !q && p.st.cls.run != 0;
   if (launches) *launches += 5;
   if (g && q) return launch_variant<true, true, false>(p, sms, smem, stream);

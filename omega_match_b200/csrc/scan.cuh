@@ -87,12 +87,12 @@ struct ScanParams {
   uint32_t tail_byte;  // value assumed at position seg_len (plain mode)
   // window mode (the store has a transform flag): buf holds SOURCE bytes, tiles are 4 KiB of one window
   const WindowDesc *windows; // per window of the launch, or nullptr (see WindowDesc)
+  uint32_t *win_extent;      // per window of the launch, or nullptr: the scan adds every chunk's kept bytes (transform.cu ghost_update_launch)
   uint64_t win_buf_off;  // buffer offset of the first source byte of window 0
   uint64_t win_src_base; // global source offset of window 0
   uint64_t win_src_len;  // source bytes of the launch's windows (the last one may be short)
   uint32_t tiles_per_win;
   uint32_t store_flags;  // kFlagIgnoreCase | kFlagIgnorePunct | kFlagElideSpace of the store
-  uint32_t priv;         // plain stores: 1 = chunks are copied into the warp's private buffer before the scan
   // tiles
   uint32_t num_tiles;             // tiles of this launch
   ChunkDesc *chunk_desc;          // [num_tiles * kTileChunks] written by the scan
@@ -125,14 +125,13 @@ inline uint64_t temp_slack_entries(int sms) { return uint64_t(sms) * kScanWarps 
 
 struct ScanGeometry {
   uint32_t stages = 0, chunk_cap = 0;
-  bool priv = false; // chunks are scanned in the warps' private buffers
 };
 constexpr uint32_t kPrivStagesMax = 6; // ring depth with private chunk buffers
 
 size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap, bool priv);
 // chooses ring depth and staging capacity for the shared memory there is; stages == 0 if the
 // filters do not fit at all
-ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit, bool want_priv);
+ScanGeometry scan_pick_geometry(const DeviceStore &st, size_t smem_limit);
 // scan -> prefix over the chunk counts (two kernels) -> placement of the records in final order
 // -> redo pass (exits at once when no chunk overflowed)
 cudaError_t scan_launch(const ScanParams &p, int sms, cudaStream_t stream, uint32_t *launches);

@@ -103,14 +103,14 @@ struct StageInfo {
   unsigned long long p0;    // position of the tile's first byte inside its segment (the haystack / its window)
   long long boff;           // buffer offset of that byte
   uint32_t tile;            // launch-local tile index, kNoTile = no more work
-  uint32_t tail;            // the byte assumed behind the end of the segment
-  uint32_t win;
   uint32_t staged;          // bytes valid behind p0 in the stage buffer
+  uint32_t tail;            // the byte assumed behind the end of the segment   (tail, win: one 8-byte load)
+  uint32_t win;             // window of the launch the tile belongs to
   uint32_t seq;             // tile iteration of the CTA this entry describes (written first)
   uint32_t stage_par;       // stage of the ring that holds the tile | parity of its mbarrier phase << 16
   uint32_t _pad[2];
 };
-static_assert(sizeof(StageInfo) == 64, "StageInfo is 64 bytes");
+static_assert(sizeof(StageInfo) == 64 && offsetof(StageInfo, tail) % 8 == 0 && offsetof(StageInfo, rem0) % 8 == 0, "StageInfo layout");
 
 // What the matching code knows about the bytes it works on: a whole tile in its stage buffer
 // (positions relative to the tile) or one chunk in a warp's private buffer (relative to the chunk).
@@ -290,8 +290,11 @@ __device__ __forceinline__ void build_copy(const StageInfo &I, uint32_t src32, u
 // stage buffer; P.buf + I.boff + cbase is the chunk's first source byte in global memory.  The 640
 // source bytes are taken in five rounds of 128 (lane l: bytes 4l .. 4l+3 of the round), so that the
 // kept bytes of a round follow those of the round before.
+// `first_pass`: the chunk is built for the first time (the scan itself, not a second evaluation): its
+// kept bytes are added to the window's extent when the launch asks for that.
 __device__ __forceinline__ void build_xf(const ScanParams &P, const StageInfo &I, uint32_t src32, uint32_t cbase,
-                                         uint32_t back, uint32_t priv32, uint32_t xf32, uint32_t lane, TileCtx &T) {
+                                         uint32_t back, uint32_t priv32, uint32_t xf32, uint32_t lane, bool first_pass,
+                                         TileCtx &T) {
   const uint32_t sf = P.store_flags;
   const bool ci = sf & kFlagIgnoreCase, ip = sf & kFlagIgnorePunct, ew = sf & kFlagElideSpace;
   const uint32_t s0 = (uint32_t)I.p0 + cbase;     // window-relative source offset of the chunk
@@ -393,8 +396,10 @@ __device__ __forceinline__ void build_xf(const ScanParams &P, const StageInfo &I
     if (bal_has) cin = (bal_last >> (31 - __clz(bal_has))) & 1u;
     total += n_round;
   }
-  if (own >= (uint32_t)kPrivData) k0 = total; // (cannot happen: own <= 512 < 640)
-  if (lane == 0) sts8(priv32 + kTilePre - 1, prevb);
+  if (lane == 0) {
+    sts8(priv32 + kTilePre - 1, prevb);
+    if (first_pass && P.win_extent && k0) atomicAdd(P.win_extent + I.win, k0); // bytes the reference writes into its scratch buffer
+  }
 
   T.sb32 = priv32;
   T.gbase = I.gbase + cbase;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kStatsThreads) stats_window_kernel(const __gri
     TileCtx T;
     if (xf32) {
       const uint32_t back = cbase + (I.boff >= (long long)kTilePre ? (uint32_t)kTilePre : (uint32_t)I.boff);
-      build_xf(P, I, smem_u32(buf) + kTilePre, cbase, back, priv32, xf32, lane, T);
+      build_xf(P, I, smem_u32(buf) + kTilePre, cbase, back, priv32, xf32, lane, false, T);
     } else {
       build_copy<true>(I, smem_u32(buf) + kTilePre, cbase, priv32, lane, T);
     }

@@ -39,43 +39,61 @@ constexpr uint32_t kTfBlocksPerWin = kWindowBytes / kTfBlockBytes;   // 1024
 static_assert(kTfBlocksPerWin == kTfBlocksPerWindow, "transform.cuh");
 constexpr uint32_t kTfUnresolved = 0xFFFFFFFFu;
 
-// One 4 KiB block of a window.  WRITE = false: summary with carry 0 -> P.blocks[].
-// WRITE = true: carry and first index from P.blocks[] (resolved); the block's kept bytes whose
-// normalised index lies in [lo, hi) of the visible part of its window go to P.ghost.
-template <bool WRITE>
-__global__ void __launch_bounds__(kTfThreads) transform_block_kernel(TransformParams P, const uint2 *visible, uint32_t n_windows) {
+// One 4 KiB block of a window, 16 source bytes per thread.
+//   kCount: summary with carry 0 -> P.blocks[] (all blocks, or -- `visible` given -- only those of
+//           windows that have a visible part);
+//   kWrite: carry and first index from P.blocks[] (resolved); the block's kept bytes whose
+//           normalised index lies in the visible part [lo, hi) of its window go to P.ghost;
+//   kPick : CTA w evaluates the block plan[w] names and stores the normalised byte at index
+//           plan[w].z as windows[w].tail.
+enum TfMode : int { kCount = 0, kWrite = 1, kPick = 2 };
+template <int MODE>
+__global__ void __launch_bounds__(kTfThreads) transform_block_kernel(TransformParams P, const uint2 *visible,
+                                                                     const uint4 *plan, uint32_t n_windows) {
   __shared__ uint32_t s_cnt[kTfWarps];   // kept bytes per warp
   __shared__ uint32_t s_has[kTfWarps];   // warp saw a non-skipped byte
   __shared__ uint32_t s_last[kTfWarps];  // ... and the last one was whitespace
   __shared__ uint32_t s_first[kTfWarps]; // ... and the first one was whitespace
   __shared__ uint32_t s_lastb[kTfWarps]; // mapped value of the warp's last non-skipped byte
 
-  for (uint64_t gb = blockIdx.x; gb < (uint64_t)n_windows * kTfBlocksPerWin; gb += gridDim.x) {
+  const uint64_t n_items = MODE == kPick ? n_windows : (uint64_t)n_windows * kTfBlocksPerWin;
+  for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    uint64_t gb = item;
+    uint32_t pick_idx = 0;
+    if (MODE == kPick) {
+      const uint4 pl = plan[item];
+      if (!pl.w) continue;
+      gb = (uint64_t)pl.x * kTfBlocksPerWin + pl.y;
+      pick_idx = pl.z;
+    }
     const uint32_t win = (uint32_t)(gb / kTfBlocksPerWin), bidx = (uint32_t)(gb % kTfBlocksPerWin);
     const uint64_t src_base = P.src_off + (uint64_t)win * kWindowBytes;
     const uint64_t remain = P.src_len - (uint64_t)win * kWindowBytes;
     const uint32_t wlen = remain < kWindowBytes ? (uint32_t)remain : kWindowBytes;
     const uint32_t blk = bidx * kTfBlockBytes;
     TfBlock &B = P.blocks[gb];
-    if (blk >= wlen) { // past the end of a short last window
-      if (!WRITE && threadIdx.x == 0) B = TfBlock{0, 0, 0, 0};
-      continue;
-    }
     uint32_t vis_lo = 0, vis_hi = 0;
-    if (WRITE) { // does the block hold a visible byte at all?
+    if (MODE != kPick && visible) {
       const uint2 v = visible[win];
       vis_lo = v.x;
       vis_hi = v.y;
+      if (vis_hi <= vis_lo) continue; // nothing of this window is visible
+    }
+    if (blk >= wlen) { // past the end of a short last window
+      if (MODE == kCount && threadIdx.x == 0) B = TfBlock{0, 0, 0, 0};
+      continue;
+    }
+    if (MODE == kWrite) { // does the block hold a visible byte at all?
       // (the resolve pass gave every block of the window its first index, empty blocks included)
       const uint32_t b0 = B.out_base, b1 = bidx + 1 < kTfBlocksPerWin ? P.blocks[gb + 1].out_base : 0xFFFFFFFFu;
-      if (vis_hi <= vis_lo || b0 >= vis_hi || b1 <= vis_lo) continue;
+      if (b0 >= vis_hi || b1 <= vis_lo) continue;
     }
     const uint8_t *src = P.src + src_base;
     const bool ci = P.flags & kFlagIgnoreCase, ip = P.flags & kFlagIgnorePunct, ew = P.flags & kFlagElideSpace;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t carry_space = WRITE ? (B.flags >> 8) & 1u : 0u; // transform_table.c:54: 0 at the start of a window
-    const uint32_t out_base = WRITE ? B.out_base : 0u;
+    const uint32_t carry_space = MODE != kCount ? (B.flags >> 8) & 1u : 0u; // transform_table.c:54: 0 at the start of a window
+    const uint32_t out_base = MODE != kCount ? B.out_base : 0u;
 
     const uint32_t i0 = blk + tid * 16;
     uint32_t bytes[4] = {0, 0, 0, 0};
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(kTfThreads) transform_block_kernel(TransformPa
       s_has[warp] = bal_has != 0;
       s_last[warp] = bal_has ? ((bal_last >> (31 - __clz(bal_has))) & 1u) : 0u;
     }
-    if (!WRITE) { // what the resolve pass needs about the two ends of the block
+    if (MODE == kCount) { // what the resolve pass needs about the two ends of the block
       const uint32_t t_first = t_has ? ((act_space >> (__ffs(nonskip) - 1)) & 1u) : 0u;
       const uint32_t kl = t_has ? 31 - __clz(nonskip) : 0;
       const uint32_t t_lastb = (mapped[kl >> 2] >> (8 * (kl & 3))) & 0xFFu;
@@ -174,7 +192,7 @@ __global__ void __launch_bounds__(kTfThreads) transform_block_kernel(TransformPa
     }
     const uint32_t warp_excl = __shfl_sync(kFull, wincl - wsum, warp);
     const uint32_t block_total = __shfl_sync(kFull, wincl, 31);
-    if (!WRITE) {
+    if (MODE == kCount) {
       if (tid == 0) {
         TfBlock b;
         b.count = block_total; // with carry 0
@@ -190,13 +208,18 @@ __global__ void __launch_bounds__(kTfThreads) transform_block_kernel(TransformPa
       }
       continue;
     }
-    // the visible kept bytes of this thread -> the image
-    uint32_t o = out_base + warp_excl + (incl - cnt); // normalised index of the thread's first kept byte
+    // this thread's kept bytes by normalised index
+    uint32_t o = out_base + warp_excl + (incl - cnt);
     uint32_t kk = keep;
     while (kk) {
       const uint32_t k = __ffs(kk) - 1;
       kk &= kk - 1;
-      if (o >= vis_lo && o < vis_hi) P.ghost[o] = (uint8_t)(mapped[k >> 2] >> (8 * (k & 3)));
+      const uint32_t byte = (mapped[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+      if (MODE == kWrite) {
+        if (o >= vis_lo && o < vis_hi) P.ghost[o] = (uint8_t)byte;
+      } else if (o == pick_idx) {
+        P.windows[item].tail = byte;
+      }
       ++o;
     }
   }
@@ -204,9 +227,10 @@ __global__ void __launch_bounds__(kTfThreads) transform_block_kernel(TransformPa
 
 // One warp per window walks the block summaries: carry into every block, its first normalised
 // index, the window's length, the trailing-space trim (transform_table.c:82-84), the descriptor.
-__global__ void transform_resolve_kernel(TransformParams P, uint32_t n_windows) {
+__global__ void transform_resolve_kernel(TransformParams P, uint32_t n_windows, const uint2 *visible) {
   const uint32_t win = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (win >= n_windows) return;
+  if (visible && visible[win].y <= visible[win].x) return; // (only the windows the image needs)
   TfBlock *blocks = P.blocks + (size_t)win * kTfBlocksPerWin;
   uint32_t carry = 0, base = 0, lastb = 0, any = 0;
   for (uint32_t b0 = 0; b0 < kTfBlocksPerWin; b0 += 32) {
@@ -236,7 +260,7 @@ __global__ void transform_resolve_kernel(TransformParams P, uint32_t n_windows) 
       any = 1;
     }
   }
-  if (lane == 0) {
+  if (lane == 0 && !visible) {
     const bool ew = P.flags & kFlagElideSpace;
     // the last byte of the normalised window: ' ' when the window ends in an elided run,
     // else the mapped value of its last non-skipped byte
@@ -252,64 +276,42 @@ __global__ void transform_resolve_kernel(TransformParams P, uint32_t n_windows) 
   }
 }
 
-// Byte at normalised index m of window v (m < its extent): the block that holds it, then a walk
-// over the block's source bytes from the block's resolved carry on.  One thread.
-__device__ uint32_t norm_byte_at(const TransformParams &P, uint32_t v, uint32_t m) {
-  const TfBlock *blocks = P.blocks + (size_t)v * kTfBlocksPerWin;
-  // the last block whose first index is <= m (first indices never decrease; blocks without a kept
-  // byte share theirs with the next one)
-  uint32_t lo = 0, hi = kTfBlocksPerWin;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) / 2;
-    if (blocks[mid].out_base <= m) lo = mid; else hi = mid;
-  }
-  const bool ci = P.flags & kFlagIgnoreCase, ip = P.flags & kFlagIgnorePunct, ew = P.flags & kFlagElideSpace;
-  const uint64_t remain = P.src_len - (uint64_t)v * kWindowBytes;
-  const uint32_t wlen = remain < kWindowBytes ? (uint32_t)remain : kWindowBytes;
-  const uint8_t *src = P.src + P.src_off + (uint64_t)v * kWindowBytes;
-  // (a block may hold no kept byte at all; walking on into the following blocks is harmless)
-  uint32_t idx = blocks[lo].out_base, in_space = (blocks[lo].flags >> 8) & 1u;
-  for (uint32_t i = lo * kTfBlockBytes; i < wlen; ++i) {
-    uint32_t c;
-    const ByteAction a = classify_byte(src[i], ci, ip, ew, &c);
-    if (a == kSkip) continue;
-    if (a == kSpace) {
-      if (in_space) continue;
-      in_space = 1;
-    } else {
-      in_space = 0;
-    }
-    if (idx == m) return c;
-    ++idx;
-  }
-  return 0;
-}
-
 // tail(w) for windows that were not trimmed: the byte at index M_w left behind by the most
-// recent earlier window whose written extent exceeds M_w, else the ghost image.
-__global__ void window_tails_kernel(TransformParams P, uint32_t n_windows) {
+// recent earlier window whose written extent exceeds M_w, else the ghost image.  One
+// thread per window finds WHERE that byte is -- plan[w] = {window, block, index, 1} -- and the pick
+// pass of transform_block_kernel normalises that one block to read it.
+__global__ void window_tails_plan_kernel(TransformParams P, uint32_t n_windows, uint4 *plan) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_windows) return;
+  plan[w] = make_uint4(0, 0, 0, 0);
   const WindowDesc d = P.windows[w];
   if (d.tail != kTfUnresolved) return;
   const uint32_t m = d.norm_len;
-  uint32_t t = P.ghost[m];
   for (uint32_t v = w; v-- > 0;) {
     if (P.windows[v].extent > m) {
-      t = norm_byte_at(P, v, m);
-      break;
+      // the last block whose first index is <= m (first indices never decrease; blocks without a
+      // kept byte share theirs with the next one, so the block found holds index m)
+      const TfBlock *blocks = P.blocks + (size_t)v * kTfBlocksPerWin;
+      uint32_t lo = 0, hi = kTfBlocksPerWin;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (blocks[mid].out_base <= m) lo = mid; else hi = mid;
+      }
+      plan[w] = make_uint4(v, lo, m, 1);
+      return;
     }
   }
-  P.windows[w].tail = t;
+  P.windows[w].tail = P.ghost[m];
 }
 
 // visible[v] = the range of normalised indices of window v that are still in the scratch buffer
-// after the launch's last window: [extent of the longest later window, own extent).
-__global__ void visible_ranges_kernel(TransformParams P, uint32_t n_windows, uint2 *visible) {
+// after the launch's last window: [extent of the longest later window, own extent).  The extents
+// come from the window descriptors or -- launches without them -- from what the scan counted.
+__global__ void visible_ranges_kernel(TransformParams P, uint32_t n_windows, const uint32_t *extents, uint2 *visible) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint32_t mx = 0;
   for (uint32_t v = n_windows; v-- > 0;) {
-    const uint32_t e = P.windows[v].extent;
+    const uint32_t e = extents ? extents[v] : P.windows[v].extent;
     visible[v] = make_uint2(mx, e > mx ? e : mx);
     if (e > mx) mx = e;
   }
@@ -370,12 +372,26 @@ cudaError_t window_descs_launch(const TransformParams &p, uint32_t n_windows, bo
   if (!need_tails) return cudaSuccess; // the scan needs nothing from here
   const uint64_t n_blocks = (uint64_t)n_windows * kTfBlocksPerWin;
   const unsigned grid = (unsigned)(n_blocks < (uint64_t)sms * 64 ? n_blocks : (uint64_t)sms * 64);
-  transform_block_kernel<false><<<grid, kTfThreads, 0, stream>>>(p, nullptr, n_windows);
-  transform_resolve_kernel<<<(n_windows + 3) / 4, 128, 0, stream>>>(p, n_windows);
-  window_tails_kernel<<<(n_windows + 31) / 32, 32, 0, stream>>>(p, n_windows);
-  visible_ranges_kernel<<<1, 32, 0, stream>>>(p, n_windows, p.visible);
-  transform_block_kernel<true><<<grid, kTfThreads, 0, stream>>>(p, p.visible, n_windows);
-  *launches += 5;
+  transform_block_kernel<kCount><<<grid, kTfThreads, 0, stream>>>(p, nullptr, nullptr, n_windows);
+  transform_resolve_kernel<<<(n_windows + 3) / 4, 128, 0, stream>>>(p, n_windows, nullptr);
+  window_tails_plan_kernel<<<(n_windows + 63) / 64, 64, 0, stream>>>(p, n_windows, p.plan);
+  transform_block_kernel<kPick><<<n_windows, kTfThreads, 0, stream>>>(p, nullptr, p.plan, n_windows);
+  visible_ranges_kernel<<<1, 32, 0, stream>>>(p, n_windows, nullptr, p.visible);
+  transform_block_kernel<kWrite><<<grid, kTfThreads, 0, stream>>>(p, p.visible, nullptr, n_windows);
+  *launches += 6;
+  return cudaGetLastError();
+}
+
+cudaError_t ghost_update_launch(const TransformParams &p, uint32_t n_windows, const uint32_t *extents, int sms,
+                                cudaStream_t stream, uint32_t *launches) {
+  if (n_windows == 0) return cudaSuccess;
+  const uint64_t n_blocks = (uint64_t)n_windows * kTfBlocksPerWin;
+  const unsigned grid = (unsigned)(n_blocks < (uint64_t)sms * 64 ? n_blocks : (uint64_t)sms * 64);
+  visible_ranges_kernel<<<1, 32, 0, stream>>>(p, n_windows, extents, p.visible);
+  transform_block_kernel<kCount><<<grid, kTfThreads, 0, stream>>>(p, p.visible, nullptr, n_windows);
+  transform_resolve_kernel<<<(n_windows + 3) / 4, 128, 0, stream>>>(p, n_windows, p.visible);
+  transform_block_kernel<kWrite><<<grid, kTfThreads, 0, stream>>>(p, p.visible, nullptr, n_windows);
+  *launches += 4;
   return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@ struct TransformParams {
   WindowDesc *windows;  // one per window of the launch
   TfBlock *blocks;      // kTfBlocksPerWindow per window (scratch; stores that drop bytes and have 2..4 byte patterns)
   uint2 *visible;       // one per window (scratch, same stores)
+  uint4 *plan;          // one per window (scratch, same stores): where a window's stale-tail byte is found
   uint8_t *ghost;       // kWindowBytes + 1 bytes, image of the reference's scratch buffer
   uint32_t flags;       // header flags of the store
 };
@@ -32,6 +33,11 @@ struct TransformParams {
 // Window descriptors of a launch (see transform.cu for who needs what).  need_tails: the store has
 // 2..4 byte patterns -- tails are resolved and the ghost image is brought up to date.
 cudaError_t window_descs_launch(const TransformParams &p, uint32_t n_windows, bool need_tails, int sms,
+                                cudaStream_t stream, uint32_t *launches);
+// Stores that drop bytes and have 2..4 byte patterns, launches that did NOT need the descriptors:
+// the ghost image is brought up to date AFTER the scan, from the window extents the scan counted
+// (extents[w] = kept bytes of window w); only the windows that stay visible are normalised again.
+cudaError_t ghost_update_launch(const TransformParams &p, uint32_t n_windows, const uint32_t *extents, int sms,
                                 cudaStream_t stream, uint32_t *launches);
 
 } // namespace olm

@@ -198,6 +198,34 @@ def test_window_edges_and_stale_tail(store_cache):
         check(m, o, bytes(hay3))
 
 
+@pytest.mark.parametrize("sf", [(0, 1, 0), (1, 1, 1), (0, 0, 1)])
+def test_stale_tail_across_calls_of_a_normalising_store(store_cache, sf):
+    """SURVEY H6 for stores that DROP bytes: what an earlier call -- with or without word_boundary, i.e.
+    through either way the scratch-buffer image is kept (transform.cu) -- left at index M_w of the
+    reference's scratch buffer decides a 2..4 byte match at the very end of a later, shorter haystack."""
+    path = store_cache("stale-xf", b"ab\nzq\nhello\nabc\n", sf)
+    o = Oracle.from_olm(path)
+    rng = np.random.default_rng(7)
+    with Matcher(path) as m:
+        for rnd in range(6):
+            # a long haystack: words and dropped bytes; then shorter ones that END in a short pattern
+            long_hay = bytes(rng.choice(np.frombuffer(b"abQz  ..,-q\n", dtype=np.uint8), size=int(rng.integers(3000, 9000))))
+            for flags in ({}, {"word_boundary": True}, {"longest_only": True, "no_overlap": True}):
+                check(m, o, long_hay, **flags)
+                for cut in rng.integers(5, 2500, size=4):
+                    short = long_hay[:int(cut)].rstrip(b" .,-\n") + b".ab"
+                    check(m, o, short, word_boundary=True)
+                    check(m, o, short + b"..", word_boundary=True)
+        # across 4 MiB windows: the second window is shorter than the first and ends in "zq"
+        W = WINDOW
+        hay = bytearray(rng.choice(np.frombuffer(b"abQz ,.", dtype=np.uint8), size=W + 5000).tobytes())
+        hay[-2:] = b"zq"
+        check(m, o, bytes(hay))
+        check(m, o, bytes(hay), word_boundary=True)
+        hay[W - 40:W] = b"." * 40
+        check(m, o, bytes(hay), word_boundary=True)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_stores_and_haystacks(store_cache, seed):
     """Differential fuzz against the oracle: random pattern sets (all lengths), random flags."""
