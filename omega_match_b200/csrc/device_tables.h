@@ -103,7 +103,10 @@ struct DeviceStore {
   uint32_t n_long = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0;
   uint32_t smallest = 0, largest = 0;
   uint32_t flags = 0;
+  uint32_t max_recs = 0; // most patterns behind one key (a slot's record count)
+  uint32_t coop = 0;     // 1: the scan compares the records of a key as a warp (store.cpp decides)
   ByteClass cls;
 };
+constexpr uint32_t kCoopMinRecs = 8; // from this many on the scan compares a key's records as a warp (scan.cu)
 
 } // namespace olm

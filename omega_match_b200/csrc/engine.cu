@@ -825,6 +825,8 @@ int Engine::sort_records(void *dev_records, uint64_t count) {
 }
 
 void *Engine::stream() const { return impl_->stream; }
+bool Engine::needs_window_tails() const { return (impl_->hdr.flags & kFlagAnyTransform) && impl_->has_short_234; }
+void *Engine::ghost_image() const { return impl_->ghost.p; }
 
 void *Engine::gather_buffer(size_t bytes) {
   if (cudaSetDevice(impl_->device) != cudaSuccess) return nullptr;

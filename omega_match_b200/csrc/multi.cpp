@@ -201,6 +201,20 @@ omega_match_results_t *MultiMatcher::match_host(const uint8_t *haystack, size_t 
   };
   const Header &h = engines_[0]->header();
   const bool windowed = h.flags & kFlagAnyTransform;
+  // The stale-tail bytes of SURVEY H6 (2..4 byte patterns of a transforming store under word_boundary)
+  // depend on the windows in front of a window -- which a shard does not see.  Such calls run on the
+  // first GPU alone; all other calls shard, and afterwards every engine gets the scratch-buffer image
+  // of the engine that scanned the haystack's last windows.
+  const bool tails = engines_[0]->needs_window_tails();
+  if (tails && f.word_boundary) {
+    scanned_[0] = true;
+    std::free(results->matches);
+    std::free(results);
+    omega_match_results_t *r = engines_[0]->match_host(haystack, n, f);
+    last_ = engines_[0]->timing();
+    if (r) sync_ghost(0);
+    return r;
+  }
   const std::vector<Shard> plan = plan_shards(n, N, h.largest, windowed);
   MatchFlags fs = f;
   fs.no_overlap = false; // crosses shards: once, on the gathered records
@@ -241,6 +255,12 @@ omega_match_results_t *MultiMatcher::match_host(const uint8_t *haystack, size_t 
     last_.scan_launches += t.scan_launches;
     last_.kernel_launches += t.kernel_launches;
     last_.matches_before_filter += t.matches_before_filter;
+  }
+  if (tails) {
+    int last = 0;
+    for (int g = 0; g < N; ++g)
+      if (scanned_[g]) last = g;
+    sync_ghost(last);
   }
   if (total == 0) return results;
 
@@ -295,6 +315,19 @@ omega_match_results_t *MultiMatcher::match_host(const uint8_t *haystack, size_t 
   if (!ok) return bail();
   results->count = kept;
   return results;
+}
+
+// every engine's image of the reference's scratch buffer <- the one of engine `from`
+void MultiMatcher::sync_ghost(int from) {
+  Engine *src = engines_[size_t(from)];
+  if (!src->ghost_image()) return;
+  cudaStream_t st = static_cast<cudaStream_t>(src->stream());
+  for (size_t g = 0; g < engines_.size(); ++g)
+    if ((int)g != from && engines_[g]->ghost_image())
+      cudaMemcpyPeerAsync(engines_[g]->ghost_image(), engines_[g]->device(), src->ghost_image(), src->device(),
+                          size_t(kWindowBytes) + 1, st);
+  cudaSetDevice(src->device());
+  cudaStreamSynchronize(st);
 }
 
 void MultiMatcher::collect_stats(omega_match_stats_t *s) {

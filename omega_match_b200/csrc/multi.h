@@ -34,6 +34,7 @@ public:
   int size() const { return (int)engines_.size(); }
 
 private:
+  void sync_ghost(int from);
   std::vector<Engine *> engines_;
   std::vector<bool> scanned_; // engines that took part in the last call
   olm_cuda_timing_t last_{};

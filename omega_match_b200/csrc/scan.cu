@@ -163,7 +163,9 @@ enum ChunkMode { kStageMode = 0, kCountMode = 1, kDirectMode = 2 };
 
 // XF: the store has a transform flag (window mode): chunks are case-folded or normalised into the
 // warp's private buffer; plain stores never see that code.
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF>
+// COOP: keys shared by many patterns are compared by the whole warp (verify_batch); chosen for stores
+// that have such keys (DeviceStore::max_recs), compiled out elsewhere -- the kernels are register bound.
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF, bool COOP>
 struct Scanner {
   const ScanParams &P;
   const uint32_t *g4s;
@@ -250,6 +252,7 @@ struct Scanner {
   // verify      : everything else the reference does for the position (matcher.c:782-880);
   //               `emit(len)` is called once per accepted match, longest first.
   static constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+  static constexpr uint32_t kCoopMin = kCoopMinRecs; // records behind one key from which on the warp compares them together
   struct Probe {
     uint32_t tpos, gram, bucket, flags; // gram: the position's key; flags: 1 = alive, 2 = key candidate (enough bytes left), 4 = short candidate, 8 = a start predicate failed (exact statistics only)
     uint4 kb;
@@ -319,12 +322,13 @@ struct Scanner {
     return *slot != kNoSlot || (HAS_P23 && (pr.flags & 4u));
   }
 
+  // `s` = the position's slot (when slot != kNoSlot); coop_done: the slot's records have been
+  // compared by the whole warp already (verify_batch), `emitted` tells whether one of them matched.
   template <typename Emit>
-  __device__ __forceinline__ void verify(const TileCtx &T, uint32_t tpos, uint32_t slot, bool cand_p, bool bad_start,
-                                         Emit &&emit) const {
+  __device__ __forceinline__ void verify(const TileCtx &T, uint32_t tpos, uint32_t slot, const uint4 &s_in, bool cand_p,
+                                         bool bad_start, bool coop_done, bool emitted, Emit &&emit) const {
     const uint32_t rem = T.rem0 - tpos;
     const uint32_t q = T.sb32 + kTilePre + tpos;
-    bool emitted = false;
     const bool longest = fl & kLongestOnly;
     // exact statistics: the reference counts the short matcher's hits and misses before its
     // longest filter runs (matcher.c:818-877 vs :611), so what `longest` lets this kernel skip
@@ -332,7 +336,7 @@ struct Scanner {
     const bool count_all = fl & kCountAll;
 
     if (HAS_G4 && slot != kNoSlot) {
-      const uint4 s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + slot));
+      const uint4 s = COOP ? s_in : __ldg(reinterpret_cast<const uint4 *>(P.st.slots + slot));
       const uint32_t meta = s.z; // 0 when the gram equals empty_key and matched an unused place
       if (meta != 0 && bad_start) { // exact statistics: only the 4-byte set is looked at
         if (meta & kSlotShort4) n_miss += stat_inc;
@@ -348,7 +352,7 @@ struct Scanner {
           return ((hay ^ (((unsigned long long)w1 << 32) | w0)) << drop) == 0;
         };
         if (meta & kSlotMulti) {
-          const uint32_t cnt = meta & kSlotValueMask;
+          const uint32_t cnt = coop_done ? 0u : meta & kSlotValueMask;
           for (uint32_t j = 0; j < cnt; ++j) {
             const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
             const uint32_t len = r.y;
@@ -515,17 +519,64 @@ struct Scanner {
     uint32_t at = 0, tot = 0, skip = 0;
     const uint32_t keep = stat_inc;
     bool again;
+    // the position's slot: pattern bytes 0..7 + length, or where the records of its key are
+    uint4 s = make_uint4(0, 0, 0, 0);
+    if (COOP && HAS_G4 && mine && slot != kNoSlot) s = __ldg(reinterpret_cast<const uint4 *>(P.st.slots + slot));
     do {
       uint32_t cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-      if (mine)
-        verify(T, tpos, slot, cand_p, bad_start, [&](uint32_t len) {
-          const uint32_t j = cnt - skip; // wraps to a huge value while cnt < skip
-          if (j == 0) m0 = len;
-          else if (j == 1) m1 = len;
-          else if (j == 2) m2 = len;
-          else if (j == 3) m3 = len;
-          ++cnt;
-        });
+      auto emit = [&](uint32_t len) {
+        const uint32_t j = cnt - skip; // wraps to a huge value while cnt < skip
+        if (j == 0) m0 = len;
+        else if (j == 1) m1 = len;
+        else if (j == 2) m2 = len;
+        else if (j == 3) m3 = len;
+        ++cnt;
+      };
+      // Keys shared by many patterns (name lists: hundreds of surnames behind one 4-byte prefix): the
+      // WARP compares such a key's records, 32 at a time with coalesced loads, instead of one lane
+      // walking them one dependent load after the other (probe_bucket + memcmp of matcher.c:182-255
+      // as a warp-cooperative compare).  Matches reach the owning lane in record order (longest first).
+      bool coop = false, emitted0 = false;
+      if (COOP && HAS_G4) {
+        coop = mine && s.z != 0 && !bad_start && (s.z & kSlotMulti) && (s.z & kSlotValueMask) >= kCoopMin;
+        uint32_t todo = __ballot_sync(kFull, coop);
+        while (todo) {
+          const uint32_t src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t o_tpos = __shfl_sync(kFull, tpos, src), o_first = __shfl_sync(kFull, s.w, src);
+          const uint32_t o_cnt = __shfl_sync(kFull, s.z, src) & kSlotValueMask;
+          const uint32_t oq = T.sb32 + kTilePre + o_tpos, o_rem = T.rem0 - o_tpos;
+          const unsigned long long hay = ((unsigned long long)lds_le32(oq + 4) << 32) | lds_le32(oq);
+          uint32_t ncmp = 0;
+          for (uint32_t base = 0; base < o_cnt; base += 32) {
+            const bool valid = base + lane < o_cnt;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (valid) r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + o_first + base + lane));
+            const bool fits = valid && r.y <= o_rem; // matcher.c:203
+            const uint32_t drop = r.y >= 8 ? 0u : (8u - r.y) * 8u;
+            bool ok = fits && ((hay ^ (((unsigned long long)r.w << 32) | r.x)) << drop) == 0;
+            if (ok && r.y > 8) ok = tail_equal(T, o_tpos, r.y, r.z);
+            if (ok) ok = end_ok_long(T, o_tpos, r.y);
+            const uint32_t fits_bal = __ballot_sync(kFull, fits);
+            uint32_t bal = __ballot_sync(kFull, ok);
+            const bool stop = (fl & kLongestOnly) && bal; // only the first (longest) match counts
+            if (stop) bal &= 0u - bal;
+            ncmp += __popc(stop ? fits_bal & ((bal << 1) - 1u) : fits_bal);
+            while (bal) {
+              const uint32_t b = __ffs(bal) - 1;
+              bal &= bal - 1;
+              const uint32_t len = __shfl_sync(kFull, r.y, b);
+              if (lane == src) {
+                emit(len);
+                emitted0 = true;
+              }
+            }
+            if (stop) break;
+          }
+          if (lane == src) n_cmp += ncmp * stat_inc;
+        }
+      }
+      if (mine) verify(T, tpos, slot, s, cand_p, bad_start, coop, emitted0, emit);
       if (skip == 0) { // where this lane's matches go: ballot + popc, a shuffle scan only when needed
         const uint32_t bal = __ballot_sync(kFull, cnt > 0);
         if (!bal) return 0;
@@ -922,7 +973,7 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool XF>
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool XF, bool COOP>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t S = P.stages, cap = P.chunk_cap;
@@ -993,7 +1044,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 
   // ================================ scanning warps ================================
   // (everything in shared memory is addressed by 32-bit shared-space addresses from here on)
-  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF> sc(P, L.g4s, L.p23s);
+  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF, COOP> sc(P, L.g4s, L.p23s);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t ring32 = sbase + (uint32_t)(L.ring - smem);
   const uint32_t g4_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
@@ -1110,7 +1161,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 // pass, evaluates the chunk again and writes final records at the index the prefix pass computed.
 constexpr int kRedoStage = kTilePre + kPrivData;  // 656 bytes per warp
 constexpr size_t kRedoRingBytes = ((size_t)kScanWarps * kRedoStage + 127) & ~size_t(127);
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF>
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF, bool COOP>
 __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (*P.redo_flag == 0) return;
@@ -1120,7 +1171,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
   load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
   __syncthreads();
   if (warp >= kScanWarps) return;
-  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF> sc(P, L.g4s, L.p23s);
+  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF, COOP> sc(P, L.g4s, L.p23s);
   sc.stat_inc = 0; // the main pass has counted these chunks already
   const uint32_t q1_32 = smem_u32(L.q1 + warp * kChunkBytes), q2_32 = smem_u32(L.q2 + warp * kQ2Entries);
   uint8_t *buf = L.ring + (size_t)warp * kRedoStage;
@@ -1279,16 +1330,16 @@ size_t redo_smem_bytes(const DeviceStore &st) {
          size_t(kScanWarps) * kPrivBytes + (store_normalises(st) ? size_t(kScanWarps) * kXfRowBytes : 0);
 }
 
-template <bool G, bool Q, bool C, bool XF>
+template <bool G, bool Q, bool C, bool XF, bool COOP>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
   const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
   // the lean per-candidate path covers every store, as long as no position predicate is requested
   constexpr bool can_fast = G || Q;
   const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
   if (fast)
-    scan_kernel<G, Q, C, can_fast, XF><<<grid, kScanThreads, smem, stream>>>(p);
+    scan_kernel<G, Q, C, can_fast, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
   else
-    scan_kernel<G, Q, C, false, XF><<<grid, kScanThreads, smem, stream>>>(p);
+    scan_kernel<G, Q, C, false, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const uint64_t n_chunks = (uint64_t)p.num_tiles * kTileChunks;
@@ -1299,8 +1350,17 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   place_kernel<<<n_spans, kPrefixThreads, 0, stream>>>(p);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  redo_kernel<G, Q, C, XF><<<grid, kScanThreads, redo_smem_bytes(p.st), stream>>>(p);
+  redo_kernel<G, Q, C, XF, COOP><<<grid, kScanThreads, redo_smem_bytes(p.st), stream>>>(p);
   return cudaGetLastError();
+}
+// COOP kernels exist for the stores that can have many patterns behind one key: a 4-byte key (G
+// without the class prefilter's long keys)
+template <bool G, bool Q, bool C, bool XF>
+cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
+  if constexpr (G && !C) {
+    if (p.st.coop) return launch_variant<G, Q, C, XF, true>(p, sms, smem, stream);
+  }
+  return launch_variant<G, Q, C, XF, false>(p, sms, smem, stream);
 }
 template <bool G, bool Q, bool C>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
@@ -1308,20 +1368,25 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
   return launch_variant<G, Q, C, false>(p, sms, smem, stream);
 }
 
-template <bool G, bool Q, bool C, bool XF>
+template <bool G, bool Q, bool C, bool XF, bool COOP>
 cudaError_t configure_variant(size_t smem_limit) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
   if (e != cudaSuccess) return e;
   if (G || Q) {
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     if (e != cudaSuccess) return e;
   }
-  return cudaFuncSetAttribute(redo_kernel<G, Q, C, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  return cudaFuncSetAttribute(redo_kernel<G, Q, C, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
 }
 template <bool G, bool Q, bool C>
 cudaError_t configure_variant(size_t smem_limit) {
-  const cudaError_t e = configure_variant<G, Q, C, false>(smem_limit);
-  return e != cudaSuccess ? e : configure_variant<G, Q, C, true>(smem_limit);
+  cudaError_t e = configure_variant<G, Q, C, false, false>(smem_limit);
+  if (e == cudaSuccess) e = configure_variant<G, Q, C, true, false>(smem_limit);
+  if constexpr (G && !C) {
+    if (e == cudaSuccess) e = configure_variant<G, Q, C, false, true>(smem_limit);
+    if (e == cudaSuccess) e = configure_variant<G, Q, C, true, true>(smem_limit);
+  }
+  return e;
 }
 
 } // namespace

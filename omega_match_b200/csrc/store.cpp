@@ -231,6 +231,7 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
       sl.w1 = word_of(p.off, p.len, 4);
     } else {
       sl.meta = kSlotMulti | uint32_t(m.size());
+      d.max_recs = std::max<uint32_t>(d.max_recs, uint32_t(m.size()));
       sl.ref = uint32_t(s->recs.size());
       const size_t first = s->recs.size();
       for (uint32_t i : m) {
@@ -249,6 +250,10 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     sl.meta |= kSlotShort4;
   }
   s->n_keys = uint32_t(n_keys_total);
+  // Keys with many patterns behind them are compared by the whole warp (scan.cu, COOP kernels).  That
+  // pays when such keys are the rule -- census surnames: 5.6 patterns per 4-byte key, 90 vs 73 GB/s
+  // on text -- and costs a little when they are the exception (names.txt: 2.4 per key, 327 vs 335).
+  d.coop = d.max_recs >= kCoopMinRecs && n_long >= 4 * n_keys_total ? 1u : 0u;
   if (s->recs.empty()) s->recs.push_back(Rec{0, 0, 0, 0}); // never dereferenced; keeps the upload non-empty
 
   // ---- g4: one bit per gram, >= 16 bits per key while it fits the shared-memory budget
