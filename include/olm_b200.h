@@ -195,7 +195,13 @@ int olm_cuda_match_device(const omega_list_matcher_t *matcher, const void *dev_h
  * bytes [slice_begin, slice_begin+slice_len); starts in [own_begin, own_end) are reported
  * with GLOBAL offsets; end-of-buffer predicates use `global_size`.  For stores with a
  * transform flag own_begin and slice_begin must be multiples of 4 MiB.  `no_overlap` is NOT
- * applied here (it crosses shards): call olm_cuda_no_overlap() on the gathered records. */
+ * applied here (it crosses shards): call olm_cuda_no_overlap() on the gathered records (or let
+ * olm_cuda_gather_records() do it).  Other stores: the slice must hold the shard's halo -- 16 bytes
+ * in front of own_begin (unless it is 0) and the longest pattern + 1 bytes behind own_end (up to
+ * global_size); the call fails otherwise.  One deviation from a single call over the whole haystack:
+ * the stale-tail bytes of the reference's scratch buffer (2..4 byte patterns of a transforming store
+ * under word_boundary at the very end of a 4 MiB window) are resolved against the shard's own
+ * windows and this matcher's earlier calls only -- a shard does not see the windows in front of it. */
 int olm_cuda_match_shard(const omega_list_matcher_t *matcher, const void *dev_slice,
                          uint64_t slice_begin, uint64_t slice_len, uint64_t own_begin,
                          uint64_t own_end, uint64_t global_size, const void *match_ptr_base,
@@ -255,6 +261,15 @@ int olm_cuda_gather_records(olm_cuda_comm_t *comm, const void *dev_records, uint
  * place; returns the kept count or -1.  The records may have been produced on any stream: the
  * call first waits for all work queued on the device (like olm_cuda_match_device). */
 int64_t olm_cuda_no_overlap(const omega_list_matcher_t *matcher, void *dev_records, uint64_t count);
+
+/* The result listing of the reference's CLI -- one line "offset:matched bytes\n" per record, exactly
+ * what omega_match/main.c:89-133 prints (snprintf "%zu:%.*s\n": a line's bytes stop at the first NUL
+ * of the match) -- formatted on the GPU from device records and the device-resident haystack
+ * (`dev_haystack` = device address of the haystack byte with offset `haystack_offset0`).  *dev_text is
+ * device memory owned by the matcher (valid until the next format call), *text_bytes its length. */
+int olm_cuda_format_records(const omega_list_matcher_t *matcher, const void *dev_records, uint64_t count,
+                            const void *dev_haystack, uint64_t haystack_offset0, void **dev_text,
+                            uint64_t *text_bytes);
 
 /* Sort device records by (offset ascending, length descending) -- the order of
  * radix_sort_matches(), matcher.c:258-325 -- with the library's LSD radix sort. */

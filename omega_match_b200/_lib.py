@@ -113,6 +113,7 @@ ABI = [
     ("olm_cuda_gather_records", _ci, [_vp, _vp, C.c_uint64, _ci, _ci, C.POINTER(CudaResultsC)]),
     ("olm_cuda_no_overlap", C.c_int64, [_vp, _vp, C.c_uint64]),
     ("olm_cuda_sort_records", _ci, [_vp, _vp, C.c_uint64]),
+    ("olm_cuda_format_records", _ci, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     ("olm_cuda_last_timing", _ci, [_vp, C.POINTER(CudaTimingC)]),
     ("olm_cuda_set_exact_stats", _ci, [_vp, _ci]),
     ("olm_cuda_host_alloc", _vp, [C.c_size_t]),

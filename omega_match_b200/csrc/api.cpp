@@ -313,6 +313,12 @@ int64_t olm_cuda_no_overlap(const omega_list_matcher_t *m, void *dev_records, ui
   return m->engine->no_overlap_inplace(dev_records, count);
 }
 
+int olm_cuda_format_records(const omega_list_matcher_t *m, const void *dev_records, uint64_t count,
+                            const void *dev_haystack, uint64_t haystack_offset0, void **dev_text, uint64_t *text_bytes) {
+  if (!m || !m->engine || !dev_text || !text_bytes || (count && (!dev_records || !dev_haystack))) return -1;
+  return m->engine->format_records(dev_records, count, dev_haystack, haystack_offset0, dev_text, text_bytes);
+}
+
 int olm_cuda_sort_records(const omega_list_matcher_t *m, void *dev_records, uint64_t count) {
   if (!m || !m->engine) return -1;
   return m->engine->sort_records(dev_records, count);

@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include "filters.cuh"
+#include "format.cuh"
 #include "scan.cuh"
 #include "stats.cuh"
 #include "transform.cuh"
@@ -123,7 +124,7 @@ struct EngineImpl {
   ScanGeometry geo;
   bool has_short_234 = false;
   DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
-  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, tfvisible, tfplan, tfextent, misc, windows, ghost, fscratch, gather;
+  DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, tfvisible, tfplan, tfextent, misc, windows, ghost, fscratch, gather, text;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
   uint64_t out_hint = 0;
@@ -258,7 +259,7 @@ Engine::~Engine() {
   cudaSetDevice(impl_->device);
   for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
                     &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->tfvisible, &impl_->tfplan, &impl_->tfextent, &impl_->misc,
-                    &impl_->windows, &impl_->gather, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
+                    &impl_->windows, &impl_->gather, &impl_->text, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
                     &impl_->d_slens})
     b->release();
   for (auto &ev : impl_->ev)
@@ -785,6 +786,33 @@ omega_match_results_t *Engine::match_host(const uint8_t *haystack, size_t n, con
   }
   results->count = dres.count;
   return results;
+}
+
+int Engine::format_records(const void *dev_records, uint64_t count, const void *dev_haystack, uint64_t offset0,
+                           void **dev_text, uint64_t *text_bytes) {
+  EngineImpl &E = *impl_;
+  OLM_CUDA(cudaSetDevice(E.device));
+  *dev_text = nullptr;
+  *text_bytes = 0;
+  if (count == 0) return 0;
+  OLM_CUDA(cudaDeviceSynchronize()); // records and haystack may come from any stream of the caller
+  if (E.fscratch.ensure(format_scratch_bytes(count))) return -1;
+  if (E.misc.ensure(size_t(kMaxBatches) * 8 + 256)) return -1;
+  unsigned long long *d_total =
+      reinterpret_cast<unsigned long long *>(static_cast<uint8_t *>(E.misc.p) + size_t(kMaxBatches) * 8) + 1;
+  uint32_t launches = 0;
+  unsigned long long total = 0;
+  const Record *rec = static_cast<const Record *>(dev_records);
+  const uint8_t *hay = static_cast<const uint8_t *>(dev_haystack);
+  OLM_CUDA(format_lengths_launch(rec, count, hay, offset0, E.fscratch.p, d_total, E.stream, &launches));
+  OLM_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, E.stream));
+  OLM_CUDA(cudaStreamSynchronize(E.stream));
+  if (E.text.ensure(total + 16)) return -1;
+  OLM_CUDA(format_write_launch(rec, count, hay, offset0, E.fscratch.p, static_cast<uint8_t *>(E.text.p), total, E.stream, &launches));
+  OLM_CUDA(cudaStreamSynchronize(E.stream));
+  *dev_text = E.text.p;
+  *text_bytes = total;
+  return 0;
 }
 
 int64_t Engine::no_overlap_inplace(void *dev_records, uint64_t count) {

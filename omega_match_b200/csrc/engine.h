@@ -49,6 +49,10 @@ public:
   // with the scan, device-resident records.
   int match_shard_host(const uint8_t *host_slice, const ScanRange &range, const MatchFlags &f, olm_cuda_results_t *out);
 
+  // "offset:bytes\n" for every record (the CLI's listing, main.c:89-133) as one device text buffer;
+  // dev_haystack = device address of the haystack byte with offset `offset0`
+  int format_records(const void *dev_records, uint64_t count, const void *dev_haystack, uint64_t offset0,
+                     void **dev_text, uint64_t *text_bytes);
   int64_t no_overlap_inplace(void *dev_records, uint64_t count);
   int sort_records(void *dev_records, uint64_t count);
 

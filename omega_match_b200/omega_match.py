@@ -325,6 +325,15 @@ class Matcher:
             raise RuntimeError("olm_cuda_no_overlap failed")
         return int(n)
 
+    def format_records_device(self, records_ptr: int, count: int, haystack_ptr: int, offset0: int = 0):
+        """The CLI's listing ("offset:bytes\\n" per record, main.c:89-133) formatted on the GPU ->
+        (device pointer of the text, its length)."""
+        text, n = C.c_void_p(), C.c_uint64()
+        if self._lib.olm_cuda_format_records(self._matcher, records_ptr, count, haystack_ptr, offset0,
+                                             C.byref(text), C.byref(n)) != 0:
+            raise RuntimeError("olm_cuda_format_records failed")
+        return int(text.value or 0), int(n.value)
+
     def sort_records_device(self, records_ptr: int, count: int) -> None:
         if self._lib.olm_cuda_sort_records(self._matcher, records_ptr, count) != 0:
             raise RuntimeError("olm_cuda_sort_records failed")

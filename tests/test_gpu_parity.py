@@ -501,6 +501,65 @@ def test_match_device_and_sort(store_cache):
         assert t["scan_ms"] > 0 and t["kernel_launches"] >= 1
 
 
+def test_shard_without_its_halo_is_rejected_and_empty_calls_add_no_statistics(store_cache):
+    """A byte-range shard has to bring 16 bytes in front of its first owned position and the longest
+    pattern + 1 behind the last one: the call fails instead of reading what is not there.
+    An empty haystack adds nothing to an attached statistics struct (matcher.c:887-893)."""
+    torch = pytest.importorskip("torch")
+    path = store_cache("names", inputs.golden_data("names.txt"))
+    hay = inputs.text_haystack(1 << 20, 3)
+    dev = torch.from_numpy(np.concatenate([hay, np.zeros(64, dtype=np.uint8)])).cuda()
+    torch.cuda.synchronize()
+    n, half = hay.size, 1 << 19
+    with Matcher(path) as m:
+        ok = m.match_shard(dev.data_ptr() + half - 16, half - 16, n - half + 16, half, n, n, 0)
+        assert ok[0] > 0
+        with pytest.raises(RuntimeError):  # no front halo
+            m.match_shard(dev.data_ptr() + half, half, n - half, half, n, n, 0)
+        with pytest.raises(RuntimeError):  # no back halo: the slice ends with the owned range
+            m.match_shard(dev.data_ptr(), 0, half, 0, half, n, 0)
+        m.match_arrays(hay)
+        before = m.get_match_stats()
+        assert m.match_arrays(b"").size == 0
+        assert m.get_match_stats() == before
+
+
+def test_gpu_listing_equals_the_cli_format(store_cache):
+    """`olm match` prints "offset:bytes\\n" per match with snprintf("%zu:%.*s\\n")
+    (omega_match/main.c:89-133), so a line's bytes stop at a NUL inside the match.  The same text,
+    formatted on the GPU from the device records (olm_cuda_format_records)."""
+    torch = pytest.importorskip("torch")
+    names = [p for p in inputs.golden_data("names.txt").split(b"\n") if p]
+    pats = names[:4000] + [b"ab\x00cd", b"\x00x", b"zz\x00", b"q"]
+    path = store_cache("listing", b"\n".join(pats))
+    hay = inputs.text_haystack((3 << 20) + 17, 123)
+    hay[1000:1005] = np.frombuffer(b"ab\x00cd", dtype=np.uint8)
+    hay[5000:5003] = np.frombuffer(b"zz\x00", dtype=np.uint8)
+    hay[9000:9002] = np.frombuffer(b"\x00x", dtype=np.uint8)
+    dev = torch.from_numpy(np.concatenate([hay, np.zeros(64, dtype=np.uint8)])).cuda()
+    torch.cuda.synchronize()
+    o = Oracle.from_olm(path)
+    with Matcher(path) as m:
+        for flags in ({}, {"longest_only": True, "no_overlap": True}):
+            cnt, ptr = m.match_device(dev.data_ptr(), hay.size, **flags)
+            tptr, tlen = m.format_records_device(ptr, cnt, dev.data_ptr(), 0)
+            got = bytes(torch.as_tensor(_DevBytes(tptr, tlen), device="cuda").cpu().numpy()) if tlen else b""
+            want = o.match(hay, **flags)
+            hb = hay.tobytes()
+            lines = []
+            for off, ln in zip(want["offset"].tolist(), want["len"].tolist()):
+                body = hb[off:off + ln]
+                lines.append(str(off).encode() + b":" + body.split(b"\x00")[0] + b"\n")
+            assert got == b"".join(lines)
+            assert cnt == want.size and cnt > 1000
+        assert m.format_records_device(0, 0, dev.data_ptr(), 0) == (0, 0)
+
+
+class _DevBytes:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
 def test_large_synthetic_properties(store_cache):
     """A slice of BASELINE config 5 (256 MiB, 100k patterns) generated on the device: every
     planted pattern is reported, offsets ascend, shard digest equals the single-call digest,
