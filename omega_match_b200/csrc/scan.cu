@@ -66,6 +66,17 @@ using namespace dev;
 #endif
 constexpr uint32_t kGrab = OLM_GRAB;
 static_assert(kGrab >= 1 && kTileChunks % kGrab == 0, "a grab stays inside one tile");
+// Tiles per ticket.  The producer lane takes the tickets of the NEXT group while it hands out the
+// current one, so the latency of the global atomic (~1 us under load, once per tile before) is off
+// its critical path.
+#ifndef OLM_TICKET_BATCH
+#define OLM_TICKET_BATCH 4
+#endif
+// 1: a scanning warp that is ahead of the producer sleeps on an mbarrier of the tile description
+// (hardware wait) instead of polling `seq` in shared memory.
+#ifndef OLM_DESC_BAR
+#define OLM_DESC_BAR 1
+#endif
 #ifndef OLM_CLS_SKIP_BITMAP
 #define OLM_CLS_SKIP_BITMAP 0
 #endif
@@ -77,6 +88,7 @@ struct SmemHeader {
   uint32_t chunk_ctr; // next chunk of the CTA's tile sequence
   uint32_t end_k;     // first tile iteration without a tile (kNoTile until the tickets run out)
   StageInfo info[kInfoRing];
+  uint64_t described[kInfoRing]; // OLM_DESC_BAR: phase (k / kInfoRing) of entry k % kInfoRing completes when iteration k is described
 };
 static_assert(sizeof(SmemHeader) <= kSmemHeader, "header does not fit");
 
@@ -944,11 +956,12 @@ __device__ __forceinline__ void tile_ctx(const StageInfo &I, uint32_t sb32, Tile
   T.first = I.p0 == 0;
 }
 // T = chunk `cbase` of tile I in the warp's private buffer, as the matcher has to see it
+// `back` = buffer bytes in front of the chunk's first byte that are in shared memory in front of src32
 template <bool XF>
 __device__ __forceinline__ void build_chunk(const ScanParams &P, const StageInfo &I, uint32_t src32, uint32_t cbase,
-                                            uint32_t priv32, uint32_t xf32, uint32_t lane, bool first_pass, TileCtx &T) {
+                                            uint32_t back, uint32_t priv32, uint32_t xf32, uint32_t lane, bool first_pass,
+                                            TileCtx &T) {
   if (XF && xf32) {
-    const uint32_t back = cbase + (I.boff >= (long long)kTilePre ? (uint32_t)kTilePre : (uint32_t)I.boff);
     build_xf(P, I, src32, cbase, back, priv32, xf32, lane, first_pass, T);
   } else {
     build_copy<XF>(I, src32, cbase, priv32, lane, T);
@@ -990,7 +1003,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     }
     H.chunk_ctr = 0;
     H.end_k = kNoTile;
-    for (uint32_t i = 0; i < kInfoRing; ++i) H.info[i].seq = kNoTile;
+    for (uint32_t i = 0; i < kInfoRing; ++i) {
+      H.info[i].seq = kNoTile;
+      mbar_init(&H.described[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -1003,13 +1019,24 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     // (the ring depth S is any number >= 2: stage and phase parity of an iteration are counted
     // here and handed to the scanning warps through the tile description)
     uint32_t ps = 0, ppar = 0;
+    // tickets: groups of `batch` consecutive tiles; the next group's atomic is in flight while this one is handed out
+    // (small launches: single tiles, so that no SM is left without work)
+    uint32_t batch = P.num_tiles / (gridDim.x * 16u);
+    batch = batch < 1u ? 1u : batch > (uint32_t)OLM_TICKET_BATCH ? (uint32_t)OLM_TICKET_BATCH : batch;
+    uint32_t t_next = 0, t_left = 0, t_pref = atomicAdd(P.ticket, batch);
     auto produce = [&](uint32_t k) {
       const uint32_t s = ps, par = ppar;
       if (++ps == S) {
         ps = 0;
         ppar ^= 1u;
       }
-      const uint32_t t = atomicAdd(P.ticket, 1u);
+      if (t_left == 0) {
+        t_next = t_pref;
+        t_left = batch;
+        if (t_next < P.num_tiles) t_pref = atomicAdd(P.ticket, batch);
+      }
+      const uint32_t t = t_next++;
+      --t_left;
       StageInfo &I = H.info[k % kInfoRing];
       I.stage_par = s | (par << 16);
       if (t >= P.num_tiles) {
@@ -1018,25 +1045,38 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
         *reinterpret_cast<volatile uint32_t *>(&I.seq) = k;
         if (k < H.end_k) *reinterpret_cast<volatile uint32_t *>(&H.end_k) = k;
         mbar_expect_tx(&H.full[s], 0);
+        if (OLM_DESC_BAR) mbar_arrive(&H.described[k % kInfoRing]);
         return;
       }
       fill_tile(P, t, I);
       __threadfence_block();
       *reinterpret_cast<volatile uint32_t *>(&I.seq) = k;
+      if (OLM_DESC_BAR) mbar_arrive(&H.described[k % kInfoRing]);
       copy_tile(P, I, L.ring + (size_t)s * kStageBytes, &H.full[s]);
     };
     // tiles claimed ahead: the ring depth, but not more than this CTA's fair share (small inputs)
     const uint32_t share = (P.num_tiles + gridDim.x - 1) / gridDim.x;
     const uint32_t D = share < S ? (share ? share : 1u) : S;
     for (uint32_t k = 0; k < D; ++k) produce(k);
-    uint32_t s = 0, ph = 0;
-    for (uint32_t k = 0;; ++k) {
+    uint32_t s = 0, ph = 0, k = 0;
+    for (;; ++k) {
       if (H.info[k % kInfoRing].tile == kNoTile) break;
       mbar_wait(&H.scanned[s], ph);
       produce(k + D); // stage (k + D) % S last held tile k + D - S <= k: free; so is the info entry
       if (++s == S) {
         s = 0;
         ph ^= 1;
+      }
+    }
+    if (OLM_DESC_BAR) {
+      // Iteration k is the first without a tile, and every tile before it has been scanned.  The
+      // scanning warps each take one more chunk before they see that: describe the iterations those
+      // chunks fall into as empty too (k .. k + D - 1 already are), so that nobody sleeps on a
+      // description that never comes.
+      constexpr uint32_t kBeyondEnd = (kScanWarps + kTileChunks - 1) / kTileChunks + 2;
+      for (uint32_t j = k + D; j < k + D + kBeyondEnd; ++j) {
+        H.info[j % kInfoRing].tile = kNoTile;
+        mbar_arrive(&H.described[j % kInfoRing]);
       }
     }
     return;
@@ -1057,6 +1097,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
   const uint32_t scanned32 = hdr32 + (uint32_t)offsetof(SmemHeader, scanned);
   const uint32_t ctr32 = hdr32 + (uint32_t)offsetof(SmemHeader, chunk_ctr);
   const uint32_t endk32 = hdr32 + (uint32_t)offsetof(SmemHeader, end_k);
+  const uint32_t desc32 = hdr32 + (uint32_t)offsetof(SmemHeader, described);
   const uint32_t info32 = hdr32 + (uint32_t)offsetof(SmemHeader, info);
   // plain stores are scanned in the stage buffer; stores with a transform flag in the warp's private
   // buffer, which is where case folding / normalisation happen (scan_device.cuh) -- the stage is
@@ -1073,6 +1114,18 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     c = __shfl_sync(kFull, c, 0);
     const uint32_t k = c / kTileChunks, ci0 = c % kTileChunks;
     const uint32_t I32 = info32 + (k % kInfoRing) * (uint32_t)sizeof(StageInfo);
+#if OLM_DESC_BAR
+    // Wait for the description of iteration k.  A warp sleeps here (at the first iteration that is not
+    // described yet), so no warp is ever ahead of the producer, and the producer is at most S < kInfoRing
+    // iterations ahead of the oldest chunk in flight: the barrier of entry k % kInfoRing is in the phase of
+    // iteration k or of k - kInfoRing, which the parity tells apart.
+    mbar_wait32(desc32 + 8u * (k % kInfoRing), (k / kInfoRing) & 1u);
+    const uint32_t tile = lds32(I32 + (uint32_t)offsetof(StageInfo, tile));
+    if (tile == kNoTile) break;
+    const uint32_t sp = lds32(I32 + (uint32_t)offsetof(StageInfo, stage_par));
+    const uint32_t s = sp & 0xFFFFu;
+    mbar_wait32(full32 + 8u * s, sp >> 16);
+#else
     // The mbarrier only tells two phases apart: make sure the stage is in OUR generation first.
     // (Chunks past the CTA's last tile may belong to an iteration that is never produced.)
     bool over = false;
@@ -1089,6 +1142,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     mbar_wait32(full32 + 8u * s, sp >> 16);
     const uint32_t tile = lds32(I32 + (uint32_t)offsetof(StageInfo, tile));
     if (tile == kNoTile) break;
+#endif
     StageInfo I;
     load_info(I32, I);
     const uint32_t stage_sb = ring32 + s * (uint32_t)kStageBytes;
@@ -1106,7 +1160,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     uint32_t cb = cbase; // position of the chunk inside T
     bool work = cbase < I.nscan;
     if (priv_mode) {
-      if (work) build_chunk<XF>(P, I, stage_sb + kTilePre + cbase, cbase, priv32, sc.xf32, lane, true, T);
+      // (the whole tile is in the stage: everything of it in front of the chunk, and the 16 bytes in front of the tile)
+      if (work)
+        build_chunk<XF>(P, I, stage_sb + kTilePre + cbase, cbase, cbase + (I.boff >= (long long)kTilePre ? (uint32_t)kTilePre : 0u),
+                        priv32, sc.xf32, lane, true, T);
       __syncwarp();
       if (lane == 0) mbar_arrive32(scanned32 + 8u * s); // the stage buffer is not read any more
       cb = 0;
@@ -1199,7 +1256,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
       }
       __syncwarp();
       TileCtx T;
-      build_chunk<XF>(P, I, smem_u32(buf) + kTilePre, cbase, priv32, sc.xf32, lane, false, T);
+      // (the small stage holds 16 bytes in front of the chunk; what lies further back is read from global memory)
+      build_chunk<XF>(P, I, smem_u32(buf) + kTilePre, cbase, I.boff + (long long)cbase >= (long long)kTilePre ? (uint32_t)kTilePre : 0u,
+                      priv32, sc.xf32, lane, false, T);
       // first result index: the span's base + the chunks before this one in the span
       unsigned long long base = P.span_base[ch / kPrefixSpan];
       {

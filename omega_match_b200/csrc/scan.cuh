@@ -62,7 +62,7 @@ constexpr uint32_t kChunkCapMax = 1024;             // ... at most
 constexpr int kQ1Bytes = kScanWarps * kChunkBytes * 2; // candidate queues: u16 per position of a chunk
 constexpr int kQ2Entries = 96;                      // hit queue per warp (u64 entries): 31 left over + 2 x 32 new
 constexpr int kQ2Bytes = kScanWarps * kQ2Entries * 8;
-constexpr int kSmemHeader = 16 * kMaxStages + 64 * kInfoRing + 256; // barriers, counters, stage infos (a multiple of 128)
+constexpr int kSmemHeader = 16 * kMaxStages + 72 * kInfoRing + 128; // barriers, counters, stage infos (a multiple of 128)
 constexpr uint32_t kPackLenBits = 23;               // staged entry = pos_in_chunk << 23 | len (source coordinates)
 // Private chunk buffer of a scanning warp: the chunk's bytes as the matcher sees them (copied,
 // case-folded or normalised), 16 bytes in front of position 0 and up to kPrivData bytes from it on.

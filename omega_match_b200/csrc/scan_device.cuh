@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t lds_le32(uint32_t a) {
 }
 
 // One tile of a launch: written by the producer lane of scan_kernel (or computed on the spot by the
-// other kernels), read by everyone.
+// other kernels), read by the warps that scan its chunks.
 struct StageInfo {
   unsigned long long gbase; // global haystack offset of the tile's first byte (what a record's offset counts from)
   uint32_t rem0;            // plain / case-folded: matchable bytes from the tile's first position on (capped at 2^31);
@@ -106,7 +106,7 @@ struct StageInfo {
   uint32_t staged;          // bytes valid behind p0 in the stage buffer
   uint32_t tail;            // the byte assumed behind the end of the segment   (tail, win: one 8-byte load)
   uint32_t win;             // window of the launch the tile belongs to
-  uint32_t seq;             // tile iteration of the CTA this entry describes (written first)
+  uint32_t seq;             // tile iteration of the CTA this entry describes
   uint32_t stage_par;       // stage of the ring that holds the tile | parity of its mbarrier phase << 16
   uint32_t _pad[2];
 };
@@ -286,8 +286,8 @@ __device__ __forceinline__ void build_copy(const StageInfo &I, uint32_t src32, u
   T.first = (I.p0 + cbase) == 0;
 }
 
-// normalising stores.  `back` = bytes in front of the chunk's first byte that are present in the
-// stage buffer; P.buf + I.boff + cbase is the chunk's first source byte in global memory.  The 640
+// normalising stores.  `back` = bytes in front of the chunk's first byte that are present in shared
+// memory (in front of src32); P.buf + I.boff + cbase is the chunk's first source byte in global memory.  The 640
 // source bytes are taken in five rounds of 128 (lane l: bytes 4l .. 4l+3 of the round), so that the
 // kept bytes of a round follow those of the round before.
 // `first_pass`: the chunk is built for the first time (the scan itself, not a second evaluation): its
@@ -306,10 +306,16 @@ __device__ __forceinline__ void build_xf(const ScanParams &P, const StageInfo &I
   //    front of position 0 and whether a whitespace run is open (transform_table.c:54-78)
   uint32_t cin0 = 0, prevb = 0;
   bool have_prev = false;
-  for (uint32_t done = 0; done < s0; done += 32) {
+  // (the `back` bytes in front of the chunk that are in shared memory first -- nearly always enough --
+  // then global memory, 32 bytes per round)
+  for (uint32_t done = 0; done < s0;) {
+    const bool near = done < back;
+    uint32_t upto = near ? back : done + 32u;
+    if (upto > done + 32u) upto = done + 32u;
+    if (upto > s0) upto = s0;
     const uint32_t d = done + lane;
     uint32_t c = kBeyond;
-    if (d < s0) c = d < back ? lds8(src32 - 1u - d) : (uint32_t)g0[-1 - (long long)d];
+    if (d < upto) c = near ? lds8(src32 - 1u - d) : (uint32_t)g0[-1 - (long long)d];
     const uint32_t bal = __ballot_sync(kFull, c != kBeyond && !(ip && is_punct_byte(c)));
     if (bal) {
       const uint32_t cc = __shfl_sync(kFull, c, __ffs(bal) - 1);
@@ -322,9 +328,10 @@ __device__ __forceinline__ void build_xf(const ScanParams &P, const StageInfo &I
       have_prev = true;
       break;
     }
+    done = upto;
   }
 
-  uint32_t avail = I.staged - cbase; // staged source bytes from the chunk's first byte on
+  uint32_t avail = I.staged - cbase; // source bytes in shared memory from the chunk's first byte on
   if (avail > (uint32_t)kPrivData) avail = kPrivData;
   if (avail > src_left) avail = src_left;
   const bool reached = avail == src_left;                                  // the window ends inside what is normalised here

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(kStatsThreads) stats_window_kernel(const __gri
     __syncwarp();
     TileCtx T;
     if (xf32) {
-      const uint32_t back = cbase + (I.boff >= (long long)kTilePre ? (uint32_t)kTilePre : (uint32_t)I.boff);
+      // (bytes in front of the chunk that are in `buf`; what lies further back is read from global memory)
+      const uint32_t back = I.boff + (long long)cbase >= (long long)kTilePre ? (uint32_t)kTilePre : 0u;
       build_xf(P, I, smem_u32(buf) + kTilePre, cbase, back, priv32, xf32, lane, false, T);
     } else {
       build_copy<true>(I, smem_u32(buf) + kTilePre, cbase, priv32, lane, T);
