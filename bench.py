@@ -465,13 +465,17 @@ def run_ours(args):
         n_pg = min(total, 4 * GIB)
         pageable = np.empty(n_pg + 64, dtype=np.uint8)
         pageable[:n_pg] = host[:n_pg].numpy()
-        t0 = time.perf_counter()
-        res = lib.omega_list_matcher_match(m._matcher, pageable.ctypes.data, n_pg, *flag_ints)
-        pg_dt = time.perf_counter() - t0
+        pg = []
+        for _ in range(3):  # (the first call also allocates the library's pinned staging slots)
+            t0 = time.perf_counter()
+            res = lib.omega_list_matcher_match(m._matcher, pageable.ctypes.data, n_pg, *flag_ints)
+            pg.append(time.perf_counter() - t0)
+            if res:
+                lib.omega_match_results_destroy(res)
         if res:
-            lib.omega_match_results_destroy(res)
-            e2e["pageable"] = {"value": n_pg / pg_dt / 1e9, "unit": UNIT, "bytes": n_pg,
-                               "note": "one call, haystack in ordinary (pageable) host memory"}
+            e2e["pageable"] = {"value": n_pg / min(pg[1:]) / 1e9, "first_call": n_pg / pg[0] / 1e9, "unit": UNIT, "bytes": n_pg,
+                               "host_threads": int(lib.omega_matcher_get_num_threads(m._matcher)),
+                               "note": "haystack in ordinary (pageable) host memory; best of two calls after the first"}
         del pageable
     del host
 

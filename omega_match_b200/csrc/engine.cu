@@ -90,13 +90,16 @@ int upload(DevBuf &b, const std::vector<T> &v, const T **out) {
 
 // Pageable host haystacks (main.c maps the file, the cffi wrapper copies into ordinary memory): a
 // plain cudaMemcpyAsync from such memory is a synchronous, single-threaded staged copy with no
-// overlap.  Instead worker threads copy 8 MiB pieces into the engine's own pinned slots and issue
+// overlap.  Instead worker threads copy 4 MiB pieces into the engine's own pinned slots and issue
 // the H2D copies from there, so that the CPU copy of one piece, the DMA of others and the scan of
-// the segments that are complete all run at once.
-constexpr size_t kPieceBytes = size_t(8) << 20;
+// the segments that are complete all run at once.  Up to kStageThreadsMax threads (a thread's
+// memcpy runs at a few GB/s; the PCIe link takes ~55).
+constexpr size_t kPieceBytes = size_t(4) << 20;
+constexpr int kStageThreadsMax = 16;
 struct Stager {
   std::vector<std::thread> workers;
   std::vector<uint8_t *> slots;          // 2 per worker, pinned
+  std::vector<uint8_t *> slabs;          // the pinned allocations the slots lie in
   std::vector<cudaEvent_t> slot_events;  // the slot's last copy has finished
   std::unique_ptr<std::atomic<int>[]> seg_left; // pieces of a segment not issued yet
   std::atomic<uint64_t> next_piece{0};
@@ -266,7 +269,7 @@ Engine::~Engine() {
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : impl_->seg_events) cudaEventDestroy(ev);
   for (auto &ev : impl_->stager.slot_events) cudaEventDestroy(ev);
-  for (uint8_t *p : impl_->stager.slots) cudaFreeHost(p);
+  for (uint8_t *p : impl_->stager.slabs) cudaFreeHost(p);
   if (impl_->stream) cudaStreamDestroy(impl_->stream);
   if (impl_->copy_stream) cudaStreamDestroy(impl_->copy_stream);
   delete impl_;
@@ -583,14 +586,18 @@ int Engine::stage_pageable(const uint8_t *src, size_t n, uint64_t nseg) {
   Stager &S = E.stager;
   const uint64_t n_pieces = (n + kPieceBytes - 1) / kPieceBytes;
   const uint64_t per_seg = nseg > 1 ? kSegmentBytes / kPieceBytes : n_pieces;
-  const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)E.host_threads, 8, n_pieces}));
-  while (S.slots.size() < size_t(2 * T)) {
-    uint8_t *p = nullptr;
-    cudaEvent_t ev;
-    OLM_CUDA(cudaHostAlloc(&p, kPieceBytes, cudaHostAllocDefault));
-    OLM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    S.slots.push_back(p);
-    S.slot_events.push_back(ev);
+  const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)E.host_threads, (uint64_t)kStageThreadsMax, n_pieces}));
+  if (S.slots.size() < size_t(2 * T)) { // (one pinned allocation for all the slots that are missing)
+    const size_t more = size_t(2 * T) - S.slots.size();
+    uint8_t *slab = nullptr;
+    OLM_CUDA(cudaHostAlloc(&slab, more * kPieceBytes, cudaHostAllocDefault));
+    S.slabs.push_back(slab);
+    for (size_t i = 0; i < more; ++i) {
+      cudaEvent_t ev;
+      OLM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      S.slots.push_back(slab + i * kPieceBytes);
+      S.slot_events.push_back(ev);
+    }
   }
   S.seg_left.reset(new std::atomic<int>[nseg]);
   for (uint64_t i = 0; i < nseg; ++i) {
@@ -856,9 +863,11 @@ void *Engine::stream() const { return impl_->stream; }
 bool Engine::needs_window_tails() const { return (impl_->hdr.flags & kFlagAnyTransform) && impl_->has_short_234; }
 void *Engine::ghost_image() const { return impl_->ghost.p; }
 
-void *Engine::gather_buffer(size_t bytes) {
+void *Engine::gather_buffer(size_t bytes, size_t *cap) {
   if (cudaSetDevice(impl_->device) != cudaSuccess) return nullptr;
-  if (impl_->gather.ensure(bytes ? bytes : 16)) return nullptr;
+  // (bytes == 0 with `cap`: the buffer as it is, nothing allocated)
+  if ((bytes || !cap) && impl_->gather.ensure(bytes ? bytes : 16)) return nullptr;
+  if (cap) *cap = impl_->gather.cap;
   return impl_->gather.p;
 }
 

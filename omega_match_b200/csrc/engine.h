@@ -60,7 +60,7 @@ public:
   bool needs_window_tails() const;           // transforming store with 2..4 byte patterns (transform.cu)
   void *ghost_image() const;                 // device image of the reference's scratch buffer (kWindowBytes + 1 bytes) or nullptr
   void *stream() const;                      // the matcher's cudaStream_t
-  void *gather_buffer(size_t bytes);         // device memory for gathered records (kept until the next request)
+  void *gather_buffer(size_t bytes, size_t *cap = nullptr); // device memory for gathered records (kept until a larger request); *cap = its size
   int records_to_host(void *host_dst, const void *dev_records, uint64_t count); // asynchronous, on stream()
   int sync();                                // waits for stream()
 

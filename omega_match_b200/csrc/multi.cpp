@@ -340,12 +340,32 @@ void MultiMatcher::set_exact_stats(bool on) {
 
 // ================================ (2) one process per GPU =========================================
 
+// Per-rank entry of the exchange that opens every gather: the rank's record count and -- meaningful
+// for the root only -- where its gather buffer is, how large, which buffer the other ranks have mapped,
+// and the buffer's IPC handle.
+struct alignas(16) GatherHello {
+  unsigned long long count;
+  unsigned long long buf;      // root: its gather buffer as it is now (0 = none)
+  unsigned long long cap;      // root: bytes of that buffer
+  unsigned long long exported; // root: the buffer the handle below belongs to
+  unsigned long long ok;       // this rank can use the window (0: it failed to map it once -> NCCL send/recv from now on)
+  unsigned long long _pad;
+  unsigned char handle[64];    // cudaIpcMemHandle_t of `exported`
+};
+static_assert(sizeof(GatherHello) == 112 && sizeof(cudaIpcMemHandle_t) == 64, "exchange layout");
+
 struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   Engine *engine = nullptr;
-  unsigned long long *d_counts = nullptr; // world entries
-  std::vector<unsigned long long> h_counts;
+  GatherHello *d_hello = nullptr; // world entries
+  std::vector<GatherHello> h_hello;
+  // the root's gather buffer as a window the other ranks write their records into (CUDA IPC + NVLink)
+  bool use_window = true;          // OLM_GATHER_WINDOW=0, or a rank that could not map it: NCCL send/recv instead
+  unsigned long long exported = 0; // root: the buffer whose handle is current
+  cudaIpcMemHandle_t handle{};     // root: that handle
+  unsigned long long mapped = 0;   // other ranks: root buffer (its address there) that is mapped here ...
+  void *window = nullptr;          // ... and where
 };
 
 Comm *comm_create(Engine *engine, const void *id, int rank, int world) {
@@ -355,13 +375,14 @@ Comm *comm_create(Engine *engine, const void *id, int rank, int world) {
   c->rank = rank;
   c->world = world;
   c->engine = engine;
-  c->h_counts.assign(world, 0);
+  c->h_hello.assign(world, GatherHello{});
+  if (const char *e = std::getenv("OLM_GATHER_WINDOW")) c->use_window = std::atoi(e) != 0;
   ncclUniqueId uid;
   std::memcpy(&uid, id, sizeof uid);
-  if (cudaMalloc(&c->d_counts, sizeof(unsigned long long) * world) != cudaSuccess ||
+  if (cudaMalloc(&c->d_hello, (sizeof(GatherHello) + 8) * world) != cudaSuccess ||
       nccl().CommInitRank(&c->comm, world, uid, rank) != ncclSuccess) {
     std::fprintf(stderr, "libomega_match(b200): cannot create the NCCL communicator (rank %d of %d)\n", rank, world);
-    if (c->d_counts) cudaFree(c->d_counts);
+    if (c->d_hello) cudaFree(c->d_hello);
     delete c;
     return nullptr;
   }
@@ -371,8 +392,9 @@ Comm *comm_create(Engine *engine, const void *id, int rank, int world) {
 void comm_destroy(Comm *c) {
   if (!c) return;
   cudaSetDevice(c->engine->device());
+  if (c->window) cudaIpcCloseMemHandle(c->window);
   if (c->comm) nccl().CommDestroy(c->comm);
-  if (c->d_counts) cudaFree(c->d_counts);
+  if (c->d_hello) cudaFree(c->d_hello);
   delete c;
 }
 
@@ -384,6 +406,26 @@ int comm_unique_id(void *id, size_t bytes) {
   return 0;
 }
 
+namespace {
+// every rank contributes its entry of h_hello; afterwards all entries are on every rank's host
+int exchange_hello(Comm *c, cudaStream_t st) {
+  OLM_CUDA(cudaMemcpyAsync(c->d_hello + c->rank, &c->h_hello[c->rank], sizeof(GatherHello), cudaMemcpyHostToDevice, st));
+  OLM_NCCL(nccl().AllGather(c->d_hello + c->rank, c->d_hello, sizeof(GatherHello), ncclUint8, c->comm, st));
+  OLM_CUDA(cudaMemcpyAsync(c->h_hello.data(), c->d_hello, sizeof(GatherHello) * c->world, cudaMemcpyDeviceToHost, st));
+  OLM_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+} // namespace
+
+// Gather of the per-rank record arrays (each in final order, shards ordered by rank) on `root`.
+// One exchange tells every rank all counts, hence where its records go.  Then
+//   * window path (default): the root's gather buffer is mapped into the other ranks (CUDA IPC, set up
+//     when the buffer is first made or grows) and every rank COPIES its records to their final place
+//     over NVLink with its copy engines -- all ranks at once, no kernel on any SM, nothing staged; a
+//     closing 8-byte collective on the same streams tells the root that all copies have landed;
+//   * fallback (OLM_GATHER_WINDOW=0, or a rank that cannot map the window): one group of ncclSend /
+//     ncclRecv (measured: ~290 GB/s into the root whatever the number of senders; the window path is
+//     bound by the root's NVLink ingest).
 int comm_gather(Comm *c, const void *dev_records, uint64_t count, int root, bool no_overlap, olm_cuda_results_t *out) {
   if (!c || !out || root < 0 || root >= c->world) return -1;
   Engine *E = c->engine;
@@ -392,35 +434,122 @@ int comm_gather(Comm *c, const void *dev_records, uint64_t count, int root, bool
   out->count = 0;
   out->records = nullptr;
   out->device = E->device();
-  // counts of all ranks (in place: every rank contributes its own entry)
-  const unsigned long long mine = count;
-  OLM_CUDA(cudaMemcpyAsync(c->d_counts + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
-  OLM_NCCL(nccl().AllGather(c->d_counts + c->rank, c->d_counts, 1, ncclUint64, c->comm, st));
-  OLM_CUDA(cudaMemcpyAsync(c->h_counts.data(), c->d_counts, sizeof(unsigned long long) * c->world, cudaMemcpyDeviceToHost, st));
-  OLM_CUDA(cudaStreamSynchronize(st));
+  const bool is_root = c->rank == root;
+
+  GatherHello &me = c->h_hello[c->rank];
+  me = GatherHello{};
+  me.count = count;
+  me.ok = c->use_window ? 1 : 0;
+  if (is_root) {
+    size_t cap_now = 0;
+    void *cur = E->gather_buffer(0, &cap_now); // (the buffer as it is: nothing is allocated here)
+    me.buf = reinterpret_cast<unsigned long long>(cur);
+    me.cap = cap_now;
+    me.exported = c->exported;
+    std::memcpy(me.handle, &c->handle, sizeof c->handle);
+  }
+  if (exchange_hello(c, st)) return -1;
   uint64_t total = 0;
   std::vector<uint64_t> off(c->world, 0);
+  bool window = true;
   for (int r = 0; r < c->world; ++r) {
     off[r] = total;
-    total += c->h_counts[r];
+    total += c->h_hello[r].count;
+    window = window && c->h_hello[r].ok != 0;
   }
-  if (c->rank != root) { // shards are ordered: the root lays the ranks' records out in rank order
-    if (count) OLM_NCCL(nccl().Send(dev_records, count * sizeof(Record), ncclUint8, root, c->comm, st));
-    OLM_CUDA(cudaStreamSynchronize(st));
-    return 0;
+  const uint64_t need = total * sizeof(Record);
+  uint8_t *buf = nullptr; // root: the gather buffer
+
+  if (window && total) {
+    const GatherHello root_now = c->h_hello[root];
+    // (Re)open the window when the root's buffer is too small or is not the one whose handle went round.
+    if (need > root_now.cap || root_now.buf == 0 || root_now.buf != root_now.exported) {
+      // the other ranks let go of the old mapping before the root frees the memory behind it
+      if (c->window) { // (also a rank that is the root now and was not before)
+        cudaIpcCloseMemHandle(c->window);
+        c->window = nullptr;
+        c->mapped = 0;
+      }
+      me = GatherHello{};
+      me.ok = 1;
+      if (exchange_hello(c, st)) return -1; // (barrier: every mapping is closed)
+      me = GatherHello{};
+      me.ok = 1;
+      if (is_root) {
+        size_t cap = 0;
+        // (with room to grow; at least a few MiB, so that the allocation is one of its own: the handle
+        // describes a whole allocation)
+        void *p = E->gather_buffer(need + need / 4 + (size_t(4) << 20), &cap);
+        if (p && cudaIpcGetMemHandle(&c->handle, p) == cudaSuccess) {
+          c->exported = reinterpret_cast<unsigned long long>(p);
+          me.buf = me.exported = c->exported;
+          me.cap = cap;
+          std::memcpy(me.handle, &c->handle, sizeof c->handle);
+        } else {
+          cudaGetLastError();
+          me.ok = 0;
+        }
+      }
+      if (exchange_hello(c, st)) return -1; // the new handle
+      if (!is_root && c->h_hello[root].ok) {
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, c->h_hello[root].handle, sizeof h);
+        if (cudaIpcOpenMemHandle(&c->window, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+          c->mapped = c->h_hello[root].buf;
+        } else {
+          cudaGetLastError();
+          c->window = nullptr;
+          me.ok = 0;
+        }
+      }
+      me.count = 0;
+      if (exchange_hello(c, st)) return -1; // did everybody get it?
+      for (int r = 0; r < c->world; ++r) window = window && c->h_hello[r].ok != 0;
+      if (!window) {
+        if (c->use_window && c->rank == 0)
+          std::fprintf(stderr, "libomega_match(b200): the gather window could not be mapped on every rank; using ncclSend/ncclRecv\n");
+        c->use_window = false;
+        if (!is_root && c->window) {
+          cudaIpcCloseMemHandle(c->window);
+          c->window = nullptr;
+          c->mapped = 0;
+        }
+      }
+    }
   }
-  uint8_t *buf = nullptr;
-  if (total) {
-    buf = static_cast<uint8_t *>(E->gather_buffer(total * sizeof(Record)));
-    if (!buf) return -1;
+
+  if (window && total) {
+    if (is_root) {
+      buf = static_cast<uint8_t *>(E->gather_buffer(need, nullptr));
+      if (!buf || reinterpret_cast<unsigned long long>(buf) != c->exported) return -1;
+    }
+    uint8_t *dst = is_root ? buf : static_cast<uint8_t *>(c->window);
     if (count)
-      OLM_CUDA(cudaMemcpyAsync(buf + off[root] * sizeof(Record), dev_records, count * sizeof(Record), cudaMemcpyDeviceToDevice, st));
-    OLM_NCCL(nccl().GroupStart());
-    for (int r = 0; r < c->world; ++r)
-      if (r != root && c->h_counts[r])
-        OLM_NCCL(nccl().Recv(buf + off[r] * sizeof(Record), c->h_counts[r] * sizeof(Record), ncclUint8, r, c->comm, st));
-    OLM_NCCL(nccl().GroupEnd());
+      OLM_CUDA(cudaMemcpyAsync(dst + off[c->rank] * sizeof(Record), dev_records, count * sizeof(Record), cudaMemcpyDeviceToDevice, st));
+    // every rank's copy precedes its part of this collective in stream order: when it completes on the
+    // root, all records are in the root's memory
+    uint8_t *sync = reinterpret_cast<uint8_t *>(c->d_hello + c->world); // world x 8 bytes behind the entries
+    OLM_NCCL(nccl().AllGather(sync + 8 * c->rank, sync, 8, ncclUint8, c->comm, st));
     OLM_CUDA(cudaStreamSynchronize(st));
+    if (!is_root) return 0;
+  } else {
+    if (!is_root) { // shards are ordered: the root lays the ranks' records out in rank order
+      if (count) OLM_NCCL(nccl().Send(dev_records, count * sizeof(Record), ncclUint8, root, c->comm, st));
+      OLM_CUDA(cudaStreamSynchronize(st));
+      return 0;
+    }
+    if (total) {
+      buf = static_cast<uint8_t *>(E->gather_buffer(need, nullptr));
+      if (!buf) return -1;
+      if (count)
+        OLM_CUDA(cudaMemcpyAsync(buf + off[root] * sizeof(Record), dev_records, count * sizeof(Record), cudaMemcpyDeviceToDevice, st));
+      OLM_NCCL(nccl().GroupStart());
+      for (int r = 0; r < c->world; ++r)
+        if (r != root && c->h_hello[r].count)
+          OLM_NCCL(nccl().Recv(buf + off[r] * sizeof(Record), c->h_hello[r].count * sizeof(Record), ncclUint8, r, c->comm, st));
+      OLM_NCCL(nccl().GroupEnd());
+      OLM_CUDA(cudaStreamSynchronize(st));
+    }
   }
   uint64_t kept = total;
   if (no_overlap && total > 1) {

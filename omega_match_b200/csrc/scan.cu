@@ -752,6 +752,14 @@ struct Scanner {
         }
       }
     }
+    const uint32_t rem_c = T.rem0 - cbase; // >= 1
+    const uint32_t kbytes = P.st.key_bytes;
+    if (rem_c < (uint32_t)kChunkBytes + 8u) {
+      // only the segment's last chunks: a position with fewer than key_bytes bytes left is no key
+      // candidate (no pattern behind a key is shorter than the key: matcher.c:203 would reject them all)
+      const uint32_t fit = rem_c >= kbytes ? rem_c - kbytes + 1u : 0u, lrel = lane * 16;
+      cand &= lrel >= fit ? 0u : (fit - lrel >= 16u ? 0xFFFFu : ((1u << (fit - lrel)) - 1u));
+    }
     const uint32_t cg = cand; // gram candidates
     cand |= cp;
     if (lpos + 16 > T.nscan) cand &= lpos >= T.nscan ? 0u : ((1u << (T.nscan - lpos)) - 1u);
@@ -794,9 +802,7 @@ struct Scanner {
     const uint32_t tile_off = sb_off + kTilePre + cbase;
     const uint32_t key_shift = P.st.key_shift, g4_shift = P.st.g4_shift, empty = P.st.empty_key;
     const uint4 *keys = P.st.keys;
-    const uint32_t rem_c = T.rem0 - cbase; // >= 1
-    const uint32_t tmask = P.st.tail_mask, kbytes = P.st.key_bytes;
-    const bool near_end = rem_c < (uint32_t)kChunkBytes + 8u;
+    const uint32_t tmask = P.st.tail_mask;
     uint32_t found = 0, q2n = 0;
     constexpr int U = OLM_FAST_UNROLL;
     for (uint32_t base = 0; base < total; base += 32 * U) {
@@ -819,7 +825,6 @@ struct Scanner {
         uint32_t h = __byte_perm(__funnelshift_r(x0, x1, sh8), 0, 0x0123) * kHashMul;
         if (tmask) h ^= (__funnelshift_r(x1, lds32(a4 + 8), sh8) & tmask) * kHashMul2; // keys longer than 4 bytes
         gram[u] = h; // the key of the position
-        if (near_end) pass[u] = pass[u] && (e[u] + kbytes <= rem_c); // only the segment's last chunks
         if (HAS_CLS && !OLM_CLS_SKIP_BITMAP) {
           const uint32_t b = h >> g4_shift;
           const uint32_t word = lds32(g4_off + ((b >> 5) << 2));

@@ -1,4 +1,5 @@
 #!/bin/sh
-# N=8 validation of the bench line (weak, strong, parity, e2e with the merge)
+# N=4 validation of the bench line (weak, strong, parity, e2e with the merge)
 nvidia-smi -L | head -8
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r2l_bench_n8.json 2> gpurun_out/r2l_bench_n8.err; echo "bench n8 rc=$?"; cut -c1-600 gpurun_out/r2l_bench_n8.json; tail -4 gpurun_out/r2l_bench_n8.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 4 --steps 3 --warmup 3 > gpurun_out/r2l_bench_n4.json 2> gpurun_out/r2l_bench_n4.err; echo "bench n4 rc=$?"; cut -c1-600 gpurun_out/r2l_bench_n4.json; tail -4 gpurun_out/r2l_bench_n4.err
+timeout 600 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2l_multi.log 2>&1; echo "multi tests rc=$?"; tail -3 gpurun_out/r2l_multi.log
