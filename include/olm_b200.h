@@ -243,11 +243,15 @@ int olm_cuda_shard_plan(const omega_list_matcher_t *matcher, uint64_t global_siz
                         olm_shard_t *out);
 
 /* (2) One process per GPU.  Every rank scans its shard (olm_cuda_match_shard[_host]) and the ranks
- * gather the per-rank sorted records on `root` with NCCL over NVLink: counts by ncclAllGather, the
- * records by one group of ncclSend/ncclRecv into the root matcher's memory in rank order (= global
- * order), then -- if asked -- the no_overlap filter once on the whole.  Rank 0 makes the id
- * (128 bytes) and hands it to the other ranks by whatever means the job has.  NCCL is opened with
- * dlopen("libnccl.so.2") on first use.  Collective: every rank calls olm_cuda_gather_records(). */
+ * gather the per-rank sorted records on `root` over NVLink: one ncclAllGather tells every rank all
+ * counts, hence where its records go (rank order = global order); the root's gather buffer is
+ * mapped into the other ranks' address spaces (CUDA IPC, set up when the buffer is made or grows)
+ * and every rank copies its records to their final place with its copy engines, all ranks at once;
+ * a closing 8-byte collective tells the root that everything has landed.  Then -- if asked -- the
+ * no_overlap filter once on the whole.  OLM_GATHER_WINDOW=0 (or a rank that cannot map the window)
+ * selects one group of ncclSend/ncclRecv instead.  Rank 0 makes the id (128 bytes) and hands it to
+ * the other ranks by whatever means the job has.  NCCL is opened with dlopen("libnccl.so.2") on
+ * first use.  Collective: every rank calls olm_cuda_gather_records(). */
 typedef struct olm_cuda_comm olm_cuda_comm_t;
 int olm_cuda_comm_unique_id(void *id, size_t id_bytes);
 olm_cuda_comm_t *olm_cuda_comm_create(const omega_list_matcher_t *matcher, const void *id, int rank,

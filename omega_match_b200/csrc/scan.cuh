@@ -126,7 +126,7 @@ inline uint64_t temp_slack_entries(int sms) { return uint64_t(sms) * kScanWarps 
 struct ScanGeometry {
   uint32_t stages = 0, chunk_cap = 0;
 };
-constexpr uint32_t kPrivStagesMax = 6; // ring depth with private chunk buffers
+constexpr uint32_t kPrivStagesMax = (6u * 4096u / kTileBytes) < (uint32_t)kMaxStages ? (6u * 4096u / kTileBytes) : (uint32_t)kMaxStages; // ring depth with private chunk buffers (24 KiB of tiles)
 
 size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap, bool priv);
 // chooses ring depth and staging capacity for the shared memory there is; stages == 0 if the
