@@ -99,6 +99,13 @@ struct DeviceStore {
   uint32_t tail_mask = 0;            // the K - 4 low bytes of the little-endian word of bytes 4..7
   uint32_t g4_shift = 32, g4_words = 0;
   uint32_t p23_and = 0, p23_mul = 1, p23_shift = 32, p23_words = 0;
+  // sx: what a p23 candidate is checked against before it costs a verify (shared memory, scan.cu):
+  // words [0, 2048) bit (b0<<8|b1) = "b0 b1 is a 2-byte pattern or b0 is a 1-byte pattern" (exact),
+  // [2048, 2048 + 2^(32-sx3_shift)/32) a hashed bitmap of the 3-byte patterns (>= 64 bits per
+  // pattern; absent when there are none).  A superset test like p23, but close to exact: p23 only says
+  // "some short pattern starts with these two bytes / hashes like these three".  sx_words == 0: not used.
+  const uint32_t *sx = nullptr;
+  uint32_t sx_words = 0, sx3_shift = 32;
   uint32_t set3_mask = 0;
   uint32_t n_long = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0;
   uint32_t smallest = 0, largest = 0;

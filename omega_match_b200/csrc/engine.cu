@@ -126,7 +126,7 @@ struct EngineImpl {
   DeviceStore ds;
   ScanGeometry geo;
   bool has_short_234 = false;
-  DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2;
+  DevBuf d_keys, d_slots, d_recs, d_store, d_g4, d_p23, d_set3, d_bitmap2, d_sx;
   DevBuf hay, out, out2, chunk_desc, span_base, temp, tfblocks, tfvisible, tfplan, tfextent, misc, windows, ghost, fscratch, gather, text;
   cudaEvent_t ev[8] = {};
   olm_cuda_timing_t last{};
@@ -217,6 +217,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   ok = ok && upload(impl->d_store, staged.store, &impl->ds.store) == 0;
   ok = ok && upload(impl->d_g4, staged.g4, &impl->ds.g4) == 0;
   ok = ok && upload(impl->d_p23, staged.p23, &impl->ds.p23) == 0;
+  if (impl->ds.sx_words) ok = ok && upload(impl->d_sx, staged.sx, &impl->ds.sx) == 0;
   ok = ok && upload(impl->d_set3, staged.set3, &impl->ds.set3) == 0;
   ok = ok && upload(impl->d_bitmap2, staged.bitmap2, &impl->ds.bitmap2) == 0;
   if (const char *sp = std::getenv("OLM_HOST_SPAN_BYTES")) {
@@ -243,9 +244,26 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
   for (auto &ev : impl->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
   ok = ok && scan_configure(impl->smem_limit) == cudaSuccess;
   impl->geo = scan_pick_geometry(impl->ds, impl->smem_limit);
-  if (!ok || impl->geo.stages == 0) {
-    delete eng;
-    return fail("CUDA setup failed while uploading the store");
+  if (impl->ds.sx_words) {
+    // The short candidates' second look (DeviceStore::sx) lives in shared memory beside the filters.
+    // It pays where p23 is the weak filter -- the direct two-byte bitmap of stores with 1-byte
+    // patterns: 366 vs 339 GB/s on BASELINE configs[3] -- and costs a little where p23 is the hashed
+    // three-byte bitmap (names.txt 326 vs 339, census 89 vs 92); and it must not take the room of the
+    // tile ring or of the staging areas (census with all transform flags: chunk capacity 168 -> 64,
+    // dense chunks redone, 14.5 vs 40 GB/s).  OLM_SHORT_LOOK=0 / 1 overrides the first condition.
+    DeviceStore plain = impl->ds;
+    plain.sx_words = 0;
+    const ScanGeometry g0 = scan_pick_geometry(plain, impl->smem_limit);
+    const char *env = std::getenv("OLM_SHORT_LOOK");
+    // (the kernels with the second look exist for plain stores without the cooperative compare)
+    const bool plain_store = !(impl->hdr.flags & kFlagAnyTransform) && !impl->ds.coop;
+    const bool weak_p23 = plain_store && (env ? std::atoi(env) != 0 : impl->ds.p23_mul == 1);
+    const bool room = impl->geo.stages != 0 && (impl->geo.stages >= g0.stages || impl->geo.stages >= 8) &&
+                      impl->geo.chunk_cap >= std::min<uint32_t>(g0.chunk_cap, 256);
+    if (!weak_p23 || !room) {
+      impl->ds.sx_words = 0;
+      impl->geo = g0;
+    }
   }
   if (impl->hdr.flags & kFlagAnyTransform) {
     ok = impl->ghost.ensure(kWindowBytes + 64) == 0 && cudaMemset(impl->ghost.p, 0, impl->ghost.cap) == cudaSuccess;
@@ -260,7 +278,7 @@ Engine *Engine::create(const uint8_t *file, size_t size, int device, std::string
 Engine::~Engine() {
   if (!impl_) return;
   cudaSetDevice(impl_->device);
-  for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_set3,
+  for (DevBuf *b : {&impl_->d_keys, &impl_->d_slots, &impl_->d_recs, &impl_->d_store, &impl_->d_g4, &impl_->d_p23, &impl_->d_sx, &impl_->d_set3,
                     &impl_->d_bitmap2, &impl_->hay, &impl_->out, &impl_->out2, &impl_->chunk_desc, &impl_->span_base, &impl_->temp, &impl_->tfblocks, &impl_->tfvisible, &impl_->tfplan, &impl_->tfextent, &impl_->misc,
                     &impl_->windows, &impl_->gather, &impl_->text, &impl_->ghost, &impl_->fscratch, &impl_->d_bloom, &impl_->d_smap,
                     &impl_->d_slens})

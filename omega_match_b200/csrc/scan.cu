@@ -177,7 +177,9 @@ enum ChunkMode { kStageMode = 0, kCountMode = 1, kDirectMode = 2 };
 // warp's private buffer; plain stores never see that code.
 // COOP: keys shared by many patterns are compared by the whole warp (verify_batch); chosen for stores
 // that have such keys (DeviceStore::max_recs), compiled out elsewhere -- the kernels are register bound.
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF, bool COOP>
+// SX: short candidates get their second look (short_look) before they cost a verify; kernels of their
+// own -- plain stores whose p23 is the weak two-byte filter -- so that the others do not carry the code.
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool XF, bool COOP, bool SX = false>
 struct Scanner {
   const ScanParams &P;
   const uint32_t *g4s;
@@ -190,6 +192,22 @@ struct Scanner {
   mutable uint32_t stat_inc = 1; // 0 while a position is evaluated a second time
 
   uint32_t xf32 = 0; // normalising stores: the warp's rows / walk state (scan_device.cuh), else 0
+  uint32_t sx32 = 0; // shared-space address of the short candidates' second look (DeviceStore::sx), 0 = not used
+
+  // A p23 candidate's second look: is one of the 1 / 2 / 3 byte patterns really a prefix of the
+  // position's bytes (gram: bytes 0..3, big endian)?  Exact for 1 and 2 bytes (one bitmap over the first
+  // two bytes), a hashed bitmap with >= 64 bits per pattern for 3.  Only what passes costs a Q2 entry
+  // and a verify (the p23 bitmap alone lets 7-11 % of all positions through on the BASELINE stores:
+  // 34-56 entries per chunk for 4-8 matches).
+  __device__ __forceinline__ bool short_look(uint32_t gram) const {
+    const uint32_t b = gram >> 16;
+    bool hit = (lds32(sx32 + ((b >> 5) << 2)) >> (b & 31)) & 1u;
+    if (P.st.n3) {
+      const uint32_t b3 = ((gram >> 8) * kHashMul) >> P.st.sx3_shift;
+      hit = hit || ((lds32(sx32 + 8192u + ((b3 >> 5) << 2)) >> (b3 & 31)) & 1u);
+    }
+    return hit;
+  }
 
   __device__ __forceinline__ Scanner(const ScanParams &p, const uint32_t *g4, const uint32_t *p23)
       : P(p), g4s(g4), p23s(p23), fl(p.flags) {}
@@ -298,6 +316,7 @@ struct Scanner {
       }
     }
     const uint32_t gram = __byte_perm(lds_le32(q), 0, 0x0123);
+    if (SX && cand_p) cand_p = short_look(gram);
     pr.flags = 1u | (cand_p ? 4u : 0u) | bad_start;
     if (HAS_G4 && cand_g && T.rem0 - tpos >= P.st.key_bytes) {
       const uint32_t h = key_hash(gram, P.st.tail_mask ? lds_le32(q + 4) & P.st.tail_mask : 0u);
@@ -822,7 +841,9 @@ struct Scanner {
         }
         const uint32_t a = tile_off + e[u], a4 = a & ~3u, sh8 = a << 3;
         const uint32_t x0 = lds32(a4), x1 = lds32(a4 + 4); // bytes 0..7 of the position from three aligned words
-        uint32_t h = __byte_perm(__funnelshift_r(x0, x1, sh8), 0, 0x0123) * kHashMul;
+        const uint32_t gbe = __byte_perm(__funnelshift_r(x0, x1, sh8), 0, 0x0123);
+        if (SX && __any_sync(kFull, shortc[u])) shortc[u] = shortc[u] && short_look(gbe);
+        uint32_t h = gbe * kHashMul;
         if (tmask) h ^= (__funnelshift_r(x1, lds32(a4 + 8), sh8) & tmask) * kHashMul2; // keys longer than 4 bytes
         gram[u] = h; // the key of the position
         if (HAS_CLS && !OLM_CLS_SKIP_BITMAP) {
@@ -913,12 +934,12 @@ __device__ __forceinline__ void copy_tile(const ScanParams &P, const StageInfo &
 struct SmemLayout {
   SmemHeader *H;
   uint8_t *ring;
-  uint32_t *g4s, *p23s, *staging;
+  uint32_t *g4s, *p23s, *sxs, *staging;
   uint16_t *q1;
   unsigned long long *q2;
   uint8_t *priv, *xf; // per warp: private chunk buffer (kPrivBytes), rows of a normalised chunk (kXfRowBytes)
 };
-// header | ring | g4 | p23 | Q2 (8-byte entries) | staging | Q1 | private chunk buffers | rows
+// header | ring | g4 | p23 | sx | Q2 (8-byte entries) | staging | Q1 | private chunk buffers | rows
 template <bool HAS_G4, bool HAS_P23>
 __device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, size_t ring_bytes, uint32_t staging_words) {
   SmemLayout L;
@@ -926,7 +947,8 @@ __device__ __forceinline__ SmemLayout carve(uint8_t *smem, const ScanParams &P, 
   L.ring = smem + kSmemHeader;
   L.g4s = reinterpret_cast<uint32_t *>(L.ring + ring_bytes);
   L.p23s = L.g4s + (HAS_G4 ? P.st.g4_words : 0);
-  L.q2 = reinterpret_cast<unsigned long long *>(L.p23s + (HAS_P23 ? P.st.p23_words : 0));
+  L.sxs = L.p23s + (HAS_P23 ? P.st.p23_words : 0);
+  L.q2 = reinterpret_cast<unsigned long long *>(L.sxs + (HAS_P23 ? P.st.sx_words : 0));
   L.staging = reinterpret_cast<uint32_t *>(L.q2 + kScanWarps * kQ2Entries);
   L.q1 = reinterpret_cast<uint16_t *>(L.staging + staging_words);
   L.priv = reinterpret_cast<uint8_t *>(L.q1) + kQ1Bytes;
@@ -984,6 +1006,9 @@ __device__ __forceinline__ void load_filters(const SmemLayout &L, const ScanPara
     const uint4 *src = reinterpret_cast<const uint4 *>(P.st.p23);
     uint4 *dst = reinterpret_cast<uint4 *>(L.p23s);
     for (uint32_t i = tid; i < P.st.p23_words / 4; i += nthreads) dst[i] = __ldg(src + i);
+    const uint4 *src2 = reinterpret_cast<const uint4 *>(P.st.sx);
+    uint4 *dst2 = reinterpret_cast<uint4 *>(L.sxs);
+    for (uint32_t i = tid; i < P.st.sx_words / 4; i += nthreads) dst2[i] = __ldg(src2 + i);
   }
 }
 
@@ -991,7 +1016,7 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool XF, bool COOP>
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool XF, bool COOP, bool SX = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t S = P.stages, cap = P.chunk_cap;
@@ -1089,7 +1114,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
 
   // ================================ scanning warps ================================
   // (everything in shared memory is addressed by 32-bit shared-space addresses from here on)
-  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF, COOP> sc(P, L.g4s, L.p23s);
+  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF, COOP, SX> sc(P, L.g4s, L.p23s);
+  if (SX) sc.sx32 = smem_u32(L.sxs);
   const uint32_t sbase = smem_u32(smem);
   const uint32_t ring32 = sbase + (uint32_t)(L.ring - smem);
   const uint32_t g4_32 = sbase + (uint32_t)(reinterpret_cast<uint8_t *>(L.g4s) - smem);
@@ -1233,7 +1259,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) redo_kernel(const __grid_cons
   load_filters<HAS_G4, HAS_P23>(L, P, tid, kScanThreads);
   __syncthreads();
   if (warp >= kScanWarps) return;
-  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF, COOP> sc(P, L.g4s, L.p23s);
+  Scanner<HAS_G4, HAS_P23, HAS_CLS, XF, COOP> sc(P, L.g4s, L.p23s); // (without the second look: it only spares verifies)
   sc.stat_inc = 0; // the main pass has counted these chunks already
   const uint32_t q1_32 = smem_u32(L.q1 + warp * kChunkBytes), q2_32 = smem_u32(L.q2 + warp * kQ2Entries);
   uint8_t *buf = L.ring + (size_t)warp * kRedoStage;
@@ -1390,7 +1416,7 @@ __global__ void __launch_bounds__(kPrefixThreads) place_kernel(const __grid_cons
 bool store_normalises(const DeviceStore &st) { return st.flags & (kFlagIgnorePunct | kFlagElideSpace); }
 
 size_t redo_smem_bytes(const DeviceStore &st) {
-  return kSmemHeader + kRedoRingBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kQ2Bytes + kQ1Bytes +
+  return kSmemHeader + kRedoRingBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + size_t(st.sx_words) * 4 + kQ2Bytes + kQ1Bytes +
          size_t(kScanWarps) * kPrivBytes + (store_normalises(st) ? size_t(kScanWarps) * kXfRowBytes : 0);
 }
 
@@ -1400,10 +1426,22 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
   // the lean per-candidate path covers every store, as long as no position predicate is requested
   constexpr bool can_fast = G || Q;
   const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
-  if (fast)
+  bool launched = false;
+  if constexpr (Q && !XF && !COOP) {
+    if (p.st.sx_words) { // (the engine switches the tables on for the stores they pay for)
+      if (fast)
+        scan_kernel<G, Q, C, can_fast, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
+      else
+        scan_kernel<G, Q, C, false, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
+      launched = true;
+    }
+  }
+  if (launched) {
+  } else if (fast) {
     scan_kernel<G, Q, C, can_fast, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
-  else
+  } else {
     scan_kernel<G, Q, C, false, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const uint64_t n_chunks = (uint64_t)p.num_tiles * kTileChunks;
@@ -1440,6 +1478,12 @@ cudaError_t configure_variant(size_t smem_limit) {
     e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
     if (e != cudaSuccess) return e;
   }
+  if constexpr (Q && !XF && !COOP) {
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, true, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    if (e != cudaSuccess) return e;
+  }
   return cudaFuncSetAttribute(redo_kernel<G, Q, C, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
 }
 template <bool G, bool Q, bool C>
@@ -1456,7 +1500,7 @@ cudaError_t configure_variant(size_t smem_limit) {
 } // namespace
 
 size_t scan_smem_bytes(const DeviceStore &st, uint32_t stages, uint32_t chunk_cap, bool priv) {
-  return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + kQ2Bytes +
+  return kSmemHeader + size_t(stages) * kStageBytes + size_t(st.g4_words) * 4 + size_t(st.p23_words) * 4 + size_t(st.sx_words) * 4 + kQ2Bytes +
          size_t(kScanWarps) * chunk_cap * 4 + kQ1Bytes + (priv ? size_t(kScanWarps) * kPrivBytes : 0) +
          (priv && store_normalises(st) ? size_t(kScanWarps) * kXfRowBytes : 0);
 }

@@ -325,6 +325,24 @@ std::string stage_store(const StoreView &v, const FilterBudget &budget, StagedSt
     if (v.bitmap2) std::memcpy(s->bitmap2.data(), v.bitmap2, 8192);
     if (v.bitmap1) std::memcpy(d.bitmap1, v.bitmap1, 32);
   }
+  // ---- sx: the short candidates' second look (device_tables.h)
+  if (v.n1 || v.n2 || v.n3) {
+    s->sx.assign(kSx3Off, 0);
+    if (v.n2) std::copy(s->bitmap2.begin(), s->bitmap2.end(), s->sx.begin());
+    for (uint32_t b0 = 0; b0 < 256 && v.n1; ++b0)
+      if (d.bitmap1[b0 >> 5] >> (b0 & 31) & 1)
+        for (uint32_t w = 0; w < 8; ++w) s->sx[b0 * 8 + w] = 0xFFFFFFFFu; // every second byte
+    if (v.n3) {
+      const uint32_t lg = std::min<uint32_t>(17, std::max<uint32_t>(10, ceil_log2(uint64_t(v.n3) * 64)));
+      d.sx3_shift = 32 - lg;
+      s->sx.resize(kSx3Off + (size_t(1) << lg) / 32, 0);
+      for (uint32_t i = 0; i < v.n3; ++i) {
+        const uint32_t b = sx3_bit(d, rd32(v.arr3 + 4ull * i));
+        s->sx[kSx3Off + (b >> 5)] |= 1u << (b & 31);
+      }
+    }
+    d.sx_words = uint32_t(s->sx.size()); // (a multiple of 4: copied to shared memory 16 bytes at a time)
+  }
   // ---- byte-class prefilter (device_tables.h): only when every pattern has >= 4 bytes
   if (v.n1 == 0 && v.n2 == 0 && v.n3 == 0 && (n_long || v.n4)) {
     uint32_t run = v.n4 ? 4 : std::min<uint32_t>(8, h.smallest);
@@ -521,15 +539,21 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
       }
     for (uint32_t c = 0; c < 256; c += 51) bad += !p23_ok((k << 8) | c);
     bad += !found;
+    if (d.sx_words) { // the second look never drops a 3-byte pattern
+      const uint32_t b = sx3_bit(d, k);
+      bad += !(s.sx[kSx3Off + (b >> 5)] >> (b & 31) & 1);
+    }
   }
   for (uint32_t w = 0; w < 65536 && v.bitmap2; ++w)
     if (v.bitmap2[w >> 3] & (1u << (w & 7))) {
       bad += !(s.bitmap2[w >> 5] >> (w & 31) & 1);
+      if (d.sx_words) bad += !(s.sx[w >> 5] >> (w & 31) & 1);
       for (uint32_t c = 0; c < 65536; c += 4099) bad += !p23_ok((w << 16) | c);
     }
   for (uint32_t b = 0; b < 256 && v.bitmap1; ++b)
     if (v.bitmap1[b >> 3] & (1u << (b & 7))) {
       bad += !(d.bitmap1[b >> 5] >> (b & 31) & 1);
+      if (d.sx_words) bad += !(s.sx[b * 8] & 1);
       for (uint32_t c = 0; c < (1u << 24); c += 65521) bad += !p23_ok((b << 24) | c);
     }
   return bad;

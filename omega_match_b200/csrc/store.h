@@ -34,7 +34,7 @@ struct StagedStore {
   std::vector<Slot> slots;  // 4 per bucket
   std::vector<Rec> recs;
   std::vector<uint8_t> store;
-  std::vector<uint32_t> g4, p23, set3, bitmap2;
+  std::vector<uint32_t> g4, p23, set3, bitmap2, sx;
   DeviceStore params; // pointer members are filled in after upload
   uint32_t n_keys = 0;
 };
@@ -69,6 +69,9 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s);
 // host mirror of the device hashing (scan.cu uses the same expressions)
 inline uint32_t key_home(const DeviceStore &d, uint32_t key) { return key >> d.key_shift; }
 inline uint32_t g4_bit(const DeviceStore &d, uint32_t key) { return key >> d.g4_shift; }
+constexpr uint32_t kSx3Off = 2048; // words of sx in front of its hashed part
+// bit of a 3-byte pattern (key3 = b0<<16|b1<<8|b2) in the hashed part of sx
+inline uint32_t sx3_bit(const DeviceStore &d, uint32_t key3) { return (key3 * kHashMul) >> d.sx3_shift; }
 inline uint32_t p23_bit(const DeviceStore &d, uint32_t gram) {
   return ((gram & d.p23_and) * d.p23_mul) >> d.p23_shift;
 }
