@@ -172,7 +172,11 @@ typedef struct {
  *                             range over them (see olm_cuda_matcher_create_multi)
  *   OLM_EXACT_STATS=1         see olm_cuda_set_exact_stats
  *   OLM_HOST_SPAN_BYTES=<n>   omega_list_matcher_match scans host haystacks longer than n bytes in
- *                             spans of n bytes (bounded device memory; same results) */
+ *                             spans of n bytes (bounded device memory; same results)
+ *   OLM_SHORT_LOOK=0|1        never / whenever there is room: the second look at candidates of the
+ *                             1..3 byte patterns (default: for stores with 1-byte patterns)
+ * and at olm_cuda_comm_create():
+ *   OLM_GATHER_WINDOW=0       gather with ncclSend/ncclRecv instead of the IPC window */
 int olm_cuda_device_count(void);
 /* Choose the GPU a matcher lives on BEFORE create (process wide default: device 0 or
  * $OLM_CUDA_DEVICE). */
