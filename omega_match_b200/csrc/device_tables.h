@@ -42,8 +42,8 @@
 namespace olm {
 
 struct alignas(16) Slot {
-  uint32_t w0;   // pattern bytes 0..3 as a little-endian word (single-pattern slots)
-  uint32_t w1;   // pattern bytes 4..7, zero padded
+  uint32_t w0;   // single-pattern slots: pattern bytes 0..3 as a little-endian word; multi: bit (b & 31) for every byte b that follows the key in one of the patterns
+  uint32_t w1;   // single: pattern bytes 4..7, zero padded; multi: the same for the byte after that (all ones: no constraint)
   uint32_t meta; // 0 = empty; see kSlot* below
   uint32_t ref;  // single: offset of the pattern in store[]; multi: first index in recs[]
 };

@@ -234,6 +234,13 @@ struct Scanner {
     return (XF && xf32) ? src_of(T, tpos + len - 1) - spos + 1 : len;
   }
 
+  // Multi-pattern slots: are bytes K and K + 1 of the position (hay = its first 8 bytes, little endian)
+  // among the bytes that follow the key in the slot's patterns (Slot::w0 / w1, store.cpp)?
+  __device__ __forceinline__ bool next_bytes_ok(unsigned long long hay, uint32_t m0, uint32_t m1) const {
+    const uint32_t k8 = P.st.key_bytes * 8u;
+    const uint32_t b0 = (uint32_t)(hay >> (k8 < 56u ? k8 : 56u)), b1 = (uint32_t)(hay >> (k8 < 48u ? k8 + 8u : 56u));
+    return ((m0 >> (b0 & 31u)) & (m1 >> (b1 & 31u)) & 1u) != 0;
+  }
   // bytes [8, len) of a candidate against the pattern store (bytes 0..7 are already equal)
   __device__ __forceinline__ bool tail_equal(const TileCtx &T, uint32_t tpos, uint32_t len, uint32_t store_off) const {
     const uint8_t *pat = P.st.store + store_off;
@@ -383,7 +390,8 @@ struct Scanner {
           return ((hay ^ (((unsigned long long)w1 << 32) | w0)) << drop) == 0;
         };
         if (meta & kSlotMulti) {
-          const uint32_t cnt = coop_done ? 0u : meta & kSlotValueMask;
+          // (none of the slot's patterns goes on with the position's next bytes: nothing to compare)
+          const uint32_t cnt = (coop_done || !next_bytes_ok(hay, s.x, s.y)) ? 0u : meta & kSlotValueMask;
           for (uint32_t j = 0; j < cnt; ++j) {
             const uint4 r = __ldg(reinterpret_cast<const uint4 *>(P.st.recs + s.w + j));
             const uint32_t len = r.y;
@@ -570,6 +578,10 @@ struct Scanner {
       bool coop = false, emitted0 = false;
       if (COOP && HAS_G4) {
         coop = mine && s.z != 0 && !bad_start && (s.z & kSlotMulti) && (s.z & kSlotValueMask) >= kCoopMin;
+        if (coop) { // (a key none of whose patterns goes on with the position's next bytes is not compared at all)
+          const uint32_t mq = T.sb32 + kTilePre + tpos;
+          coop = next_bytes_ok(((unsigned long long)lds_le32(mq + 4) << 32) | lds_le32(mq), s.x, s.y);
+        }
         uint32_t todo = __ballot_sync(kFull, coop);
         while (todo) {
           const uint32_t src = __ffs(todo) - 1;
