@@ -1413,9 +1413,7 @@ __global__ void __launch_bounds__(kPrefixThreads) place_kernel(const __grid_cons
       if (tb + n > P.temp_cap) continue; // dropped entries: the call is repeated with a larger buffer
       const uint64_t chs = c0 + g0 + src;
       const unsigned long long base = span0 + s_pre[g0 + src];
-      StageInfo I;
-      fill_tile(P, (uint32_t)(chs / kTileChunks), I);
-      const unsigned long long cb = I.gbase + (chs % kTileChunks) * kChunkBytes; // global offset of the chunk's first byte
+      const unsigned long long cb = tile_gbase(P, (uint32_t)(chs / kTileChunks)) + (chs % kTileChunks) * kChunkBytes; // global offset of the chunk's first byte
       for (uint32_t i = lane; i < n; i += 32) {
         const uint32_t e = __ldg(P.temp + tb + i);
         const unsigned long long r = base + i;

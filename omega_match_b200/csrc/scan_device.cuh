@@ -124,6 +124,15 @@ struct TileCtx {
   bool first;               // position 0 is the first byte of the segment
 };
 
+// Global haystack offset of the first byte of launch-local tile t (StageInfo::gbase without the rest).
+__device__ __forceinline__ unsigned long long tile_gbase(const ScanParams &P, uint32_t t) {
+  if (P.flags & kWindowMode) {
+    constexpr uint32_t kTilesPerWin = kWindowBytes / kTileBytes;
+    return P.win_src_base + (unsigned long long)(t / kTilesPerWin) * kWindowBytes + (unsigned long long)(t % kTilesPerWin) * kTileBytes;
+  }
+  return P.scan_begin + (unsigned long long)t * kTileBytes;
+}
+
 // Fills `I` for launch-local tile t.
 __device__ __forceinline__ void fill_tile(const ScanParams &P, uint32_t t, StageInfo &I) {
   I.tile = t;

@@ -529,6 +529,10 @@ uint64_t check_staged_store(const StoreView &v, const StagedStore &s) {
           if (rc.len == pl && rc.store_off == po) found = rc.w0 == w0 && rc.w1 == w1;
         }
         ok = ok && found;
+        // the slot's next-byte sets never rule this pattern out (scan.cu next_bytes_ok)
+        const uint32_t K = d.key_bytes;
+        if (K < 8) ok = ok && (pl > K ? (sl->w0 >> (v.patterns[po + K] & 31) & 1) != 0 : sl->w0 == 0xFFFFFFFFu);
+        if (K + 1 < 8) ok = ok && (pl > K + 1 ? (sl->w1 >> (v.patterns[po + K + 1] & 31) & 1) != 0 : sl->w1 == 0xFFFFFFFFu);
       }
       ok = ok && std::memcmp(s.store.data() + po, v.patterns + po, pl) == 0 && in_class(v.patterns + po);
       bad += !ok;
