@@ -745,7 +745,11 @@ struct Scanner {
   // patterns -- written against raw shared-memory offsets with nothing but the essentials in
   // the per-candidate rounds (the generic scan_chunk above spends ~3x the instructions there).
   //   sb_off/g4_off/p23_off/q1_off/q2_off/stage: shared-space byte addresses.
-  template <int MODE>
+  //   PRED: a start predicate is requested (word_boundary / word_prefix / line_start): it is evaluated
+  //   per candidate in front of the key probe, exactly as probe_issue does (matcher.c:770-776, :195-196,
+  //   :806-807); the end predicates live in verify() for both paths.  Exact statistics (kCountAll) need
+  //   the candidates a start predicate rejects and stay on the generic path.
+  template <int MODE, bool PRED>
   __device__ __forceinline__ uint32_t scan_chunk_fast(const TileCtx &T, uint32_t sb_off, uint32_t g4_off,
                                                       uint32_t p23_off, uint32_t q1_off, uint32_t q2_off,
                                                       uint32_t cbase, uint32_t lane, uint32_t stage, uint32_t cap,
@@ -854,6 +858,16 @@ struct Scanner {
         const uint32_t a = tile_off + e[u], a4 = a & ~3u, sh8 = a << 3;
         const uint32_t x0 = lds32(a4), x1 = lds32(a4 + 4); // bytes 0..7 of the position from three aligned words
         const uint32_t gbe = __byte_perm(__funnelshift_r(x0, x1, sh8), 0, 0x0123);
+        if (PRED) {
+          const bool at0 = T.first && cbase + e[u] == 0;
+          const uint32_t prev = lds8(a - 1), cur = gbe >> 24;
+          bool ok = true;
+          if (fl & kWordBoundary) ok = is_word_byte(cur) != (at0 ? false : is_word_byte(prev)); // matcher.c:770-776
+          if ((fl & kWordPrefix) && !at0 && is_word_byte(prev)) ok = false;                       // :195, :806
+          if ((fl & kLineStart) && !at0 && !is_line_end_byte(prev)) ok = false;                   // :196, :807
+          pass[u] = pass[u] && ok;
+          shortc[u] = shortc[u] && ok;
+        }
         if (SX && __any_sync(kFull, shortc[u])) shortc[u] = shortc[u] && short_look(gbe);
         uint32_t h = gbe * kHashMul;
         if (tmask) h ^= (__funnelshift_r(x1, lds32(a4 + 8), sh8) & tmask) * kHashMul2; // keys longer than 4 bytes
@@ -1028,7 +1042,8 @@ __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
 
-template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, bool FAST, bool XF, bool COOP, bool SX = false>
+// FAST: 0 = the generic per-candidate path, 1 = the lean path, 2 = the lean path with start predicates
+template <bool HAS_G4, bool HAS_P23, bool HAS_CLS, int FAST, bool XF, bool COOP, bool SX = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_constant__ ScanParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t S = P.stages, cap = P.chunk_cap;
@@ -1216,7 +1231,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_kernel(const __grid_cons
     }
     if (work) {
       if (FAST)
-        n = sc.template scan_chunk_fast<kStageMode>(T, T.sb32, g4_32, p23_32, q1_32, q2_32, cb, lane, stage32, cap, 0, &ovf);
+        n = sc.template scan_chunk_fast<kStageMode, FAST == 2>(T, T.sb32, g4_32, p23_32, q1_32, q2_32, cb, lane, stage32, cap, 0, &ovf);
       else
         n = sc.template scan_chunk<kStageMode>(T, cb, lane, stage32, cap, q1_32, q2_32, 0, &ovf);
     }
@@ -1433,24 +1448,30 @@ size_t redo_smem_bytes(const DeviceStore &st) {
 template <bool G, bool Q, bool C, bool XF, bool COOP>
 cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream_t stream) {
   const int grid = (int)(p.num_tiles < (uint32_t)sms ? p.num_tiles : (uint32_t)sms);
-  // the lean per-candidate path covers every store, as long as no position predicate is requested
+  // the lean per-candidate path covers every store and every flag set; only exact statistics need the
+  // generic one (they count the candidates a start predicate rejects)
   constexpr bool can_fast = G || Q;
-  const bool fast = can_fast && !(p.flags & (kWordBoundary | kWordPrefix | kWordSuffix | kLineStart | kLineEnd));
+  const int mode = !can_fast || (p.flags & kCountAll) ? 0 : (p.flags & (kWordBoundary | kWordPrefix | kLineStart)) ? 2 : 1;
   bool launched = false;
   if constexpr (Q && !XF && !COOP) {
     if (p.st.sx_words) { // (the engine switches the tables on for the stores they pay for)
-      if (fast)
-        scan_kernel<G, Q, C, can_fast, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
+      if (mode == 2)
+        scan_kernel<G, Q, C, 2, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
+      else if (mode == 1)
+        scan_kernel<G, Q, C, 1, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
       else
-        scan_kernel<G, Q, C, false, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
+        scan_kernel<G, Q, C, 0, XF, COOP, true><<<grid, kScanThreads, smem, stream>>>(p);
       launched = true;
     }
   }
   if (launched) {
-  } else if (fast) {
-    scan_kernel<G, Q, C, can_fast, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
-  } else {
-    scan_kernel<G, Q, C, false, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
+  } else if (mode == 0) {
+    scan_kernel<G, Q, C, 0, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
+  } else if constexpr (can_fast) {
+    if (mode == 2)
+      scan_kernel<G, Q, C, 2, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
+    else
+      scan_kernel<G, Q, C, 1, XF, COOP><<<grid, kScanThreads, smem, stream>>>(p);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -1482,19 +1503,24 @@ cudaError_t launch_variant(const ScanParams &p, int sms, size_t smem, cudaStream
 
 template <bool G, bool Q, bool C, bool XF, bool COOP>
 cudaError_t configure_variant(size_t smem_limit) {
-  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  const int lim = (int)smem_limit;
+  cudaError_t e = cudaFuncSetAttribute(scan_kernel<G, Q, C, 0, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
   if (e != cudaSuccess) return e;
-  if (G || Q) {
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, G || Q, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  if constexpr (G || Q) {
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, 1, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, 2, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
   }
   if constexpr (Q && !XF && !COOP) {
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, false, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, 0, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, true, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, 1, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(scan_kernel<G, Q, C, 2, XF, COOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     if (e != cudaSuccess) return e;
   }
-  return cudaFuncSetAttribute(redo_kernel<G, Q, C, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+  return cudaFuncSetAttribute(redo_kernel<G, Q, C, XF, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
 }
 template <bool G, bool Q, bool C>
 cudaError_t configure_variant(size_t smem_limit) {
