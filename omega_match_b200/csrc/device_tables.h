@@ -114,6 +114,9 @@ struct DeviceStore {
   uint32_t coop = 0;     // 1: the scan compares the records of a key as a warp (store.cpp decides)
   ByteClass cls;
 };
-constexpr uint32_t kCoopMinRecs = 8; // from this many on the scan compares a key's records as a warp (scan.cu)
+#ifndef OLM_COOP_MIN
+#define OLM_COOP_MIN 4
+#endif
+constexpr uint32_t kCoopMinRecs = OLM_COOP_MIN; // from this many on the scan compares a key's records as a warp (scan.cu)
 
 } // namespace olm
