@@ -43,6 +43,8 @@ enum ScanFlags : uint32_t {
 // Geometry of the kernel (compile-time; DESIGN.md "scan kernel").
 constexpr int kScanWarps = 31;                      // warps that scan
 constexpr int kScanThreads = 1024;                  // + producer warp (31: tickets, TMA)
+// (experiment knobs; only the defaults are covered by the GPU tests -- 2 KiB / 1 KiB tiles were measured on
+// the small stores, profiles/r2_tile_size_variants.log, and their 1 M pattern launch failed)
 #ifndef OLM_TILE_BYTES
 #define OLM_TILE_BYTES 4096
 #endif
